@@ -1,0 +1,26 @@
+// Plain argument structs of the kernels (no CUDA types: also used by the host-side
+// warp emulator that runs the PDIPM device code on the CPU in tests).
+#pragma once
+#include "srbd_pattern.h"
+
+namespace srbd {
+
+struct QpFormArgs {
+  const double* in[QP_N_IN];
+  double* out[QP_N_OUT];
+};
+
+// Arguments of the PDIPM kernel.  in[] / out[] follow sparse_pdipm_solver.py:532-534.
+struct PdipmArgs {
+  const double* in[IP_N_IN];    // Q_val, G_val, A_val, f, h, b, x, s, z, y   (B, nnz) each
+  double* out[IP_N_OUT];        // x, s, z, y, residuals(4), mu(1)
+  double* work;                 // (B, PDIPM_WORK_DOUBLES) scratch owned by the caller
+  int* iters_done;              // optional (B) per-env Newton iterations executed
+  int num_iters;                // Newton iterations per call (runtime, reference bakes 5)
+  double tol;                   // <= 0: fixed iteration count; > 0: stop when rx,rs,re,mu < tol
+  int cold_start;               // 1: ignore in[x,s,z,y]; start from x=0, s=max(h,1), z=1, y=1
+                                //    (mpc_controller_cusadi.py:138-141)
+};
+constexpr int PDIPM_WORK_DOUBLES = 704;   // dx_aff(240) dy_aff(140) ds_aff(160) dz_aff(160) + pad
+
+}  // namespace srbd

@@ -109,21 +109,26 @@ def unpack_G(G_val):
 
 
 def spd_inverse_gauss_jordan(M):
-    """In-place Gauss-Jordan inverse without pivoting (what each half-warp does)."""
+    """SPD inverse by the symmetric sweep operator, as each half-warp does it: every lane
+    keeps one full row, the (unscaled) pivot row is broadcast, all pivots 0..11 are swept
+    (giving -M^-1), and only the lower triangle is kept.  A plain Gauss-Jordan inverse is
+    not symmetric in floating point and loses ~1.5 digits once its upper half is dropped."""
     A = M.copy()
     n = A.shape[0]
-    for j in range(n):
-        d = 1.0 / A[j, j]
-        rowj = A[j, :] * d
-        rowj[j] = d
+    for p in range(n):
+        v = A[p, :].copy()
+        di = 1.0 / v[p]
         for r in range(n):
-            if r == j:
-                continue
-            f = A[r, j]
-            A[r, :] = A[r, :] - f * rowj
-            A[r, j] = -f * d
-        A[j, :] = rowj
-    return A
+            if r == p:
+                A[p, :] = v * di
+                A[p, p] = -di
+            else:
+                t = v[r] * di
+                row = A[r, :] - t * v
+                row[p] = t
+                A[r, :] = row
+    X = -A
+    return np.tril(X) + np.tril(X, -1).T
 
 
 class StructuredStep:

@@ -1,0 +1,62 @@
+// TEST-ONLY: runs the PDIPM *device* code (srbd_pdipm_core.h) on the CPU under the
+// fiber-based warp emulator, one emulated warp per environment.  Used by the CPU test
+// suite to check the kernel's indexing / data flow against the oracle without a GPU.
+// Never linked into the product library.
+#define SRBD_HOST_EMUL 1
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "srbd_stage_table.h"
+
+namespace srbd {
+static std::map<std::string, std::vector<double>> g_trace;
+static bool g_trace_on = false;
+void emul_trace(const char* tag, const double* ptr, int n) {
+  if (!g_trace_on) return;
+  WarpEmulState* st = emul_state();
+  if (st && st->cur != 0) return;   // lane 0 records
+  g_trace[tag].assign(ptr, ptr + n);
+}
+}  // namespace srbd
+
+using namespace srbd;
+
+template <bool kUniform>
+static void run_env(const PdipmArgs& A, long long e, const StageSlot* slots, int* iters) {
+  std::vector<double> smem(PdipmSmem<kUniform>::SIZE, 0.0);
+  run_warp([&](int lane) {
+    PdipmWarp<kUniform> W;
+    W.w.lane_ = lane;
+    W.sm = smem.data();
+    W.slots = slots;
+    int it = W.run(A, e);
+    if (lane == 0 && iters) *iters = it;
+  });
+}
+
+extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, double* work, int* iters_done,
+                               int B, int num_iters, double tol, int cold_start, int uniform, int trace) {
+  static StageSlot slots[SB_SIZE];
+  build_stage_slots(slots);
+  PdipmArgs A;
+  for (int i = 0; i < IP_N_IN; ++i) A.in[i] = in10[i];
+  for (int i = 0; i < IP_N_OUT; ++i) A.out[i] = out6[i];
+  A.work = work; A.iters_done = iters_done; A.num_iters = num_iters; A.tol = tol; A.cold_start = cold_start;
+  g_trace_on = trace != 0;
+  g_trace.clear();
+  for (long long e = 0; e < B; ++e) {
+    if (uniform) run_env<true>(A, e, slots, nullptr);
+    else run_env<false>(A, e, slots, nullptr);
+  }
+  return 0;
+}
+
+extern "C" int srbd_emul_trace_get(const char* tag, double* out, int n) {
+  auto it = g_trace.find(tag);
+  if (it == g_trace.end()) return -1;
+  int m = (int)it->second.size() < n ? (int)it->second.size() : n;
+  std::memcpy(out, it->second.data(), sizeof(double) * m);
+  return m;
+}
