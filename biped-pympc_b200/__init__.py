@@ -1,0 +1,16 @@
+"""biped-pympc_b200 -- B200-native batched SRBD-MPC solve (QP assembly + PDIPM).
+
+Drop-in for the hot path of rl-augmented-mpc/Biped-PyMPC: the two CusADi functions
+``qp_former`` and ``sparse_pdipm_multiple_iterations`` and the glue in
+``biped_pympc/convex_mpc/mpc_controller_cusadi.py``.  See DESIGN.md / INTEGRATION.md.
+
+The directory name contains a hyphen; import it through the ``biped_pympc_b200`` shim at
+the repository root (``import biped_pympc_b200 as bp``)."""
+from . import _native, workload  # noqa: F401
+from ._native import COLD_START, STAGE_INVARIANT, Context, SrbdError, dfma_peak, pattern, pdipm, qp_form, wrench  # noqa: F401
+from .cusadi_function import B200Function, PDIPM_FUNCTION, QP_FORMER_FUNCTION  # noqa: F401
+from .mpc_controller_b200 import MPCControllerB200, solve_tick  # noqa: F401
+from .sharding import shard_bounds, ShardedSolver  # noqa: F401
+
+__all__ = ["qp_form", "pdipm", "wrench", "Context", "B200Function", "MPCControllerB200", "solve_tick",
+           "shard_bounds", "ShardedSolver", "workload", "dfma_peak", "pattern"]

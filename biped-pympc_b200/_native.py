@@ -1,0 +1,239 @@
+"""ctypes binding of libsrbd_mpc.so (the C-ABI declared in include/srbd_mpc.h).
+
+There is no CPU fallback: if the shared object is missing the import of any compute entry
+point raises.  torch is used only for device memory and streams."""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libsrbd_mpc.so")
+
+COLD_START = 1
+STAGE_INVARIANT = 2
+
+QP_NNZ_IN = (12, 120, 120, 120, 1, 1, 1, 9, 9, 3, 3, 3, 20, 12, 12, 3, 3)
+QP_NNZ_OUT = (240, 240, 1196, 140, 280, 160)
+IP_NNZ_IN = (240, 280, 1196, 240, 160, 140, 240, 160, 160, 140)
+IP_NNZ_OUT = (240, 160, 160, 140, 4, 1)
+WORK_DOUBLES = 704
+
+_lib = None
+_P = ctypes.POINTER(ctypes.c_double)
+_PP = ctypes.POINTER(_P)
+
+EXPORTED_SYMBOLS = (
+    "srbd_version", "srbd_error_string", "srbd_last_cuda_error", "srbd_init",
+    "srbd_qp_former_nnz_in", "srbd_qp_former_nnz_out", "srbd_pdipm_nnz_in", "srbd_pdipm_nnz_out",
+    "srbd_pattern", "srbd_qp_form", "srbd_pdipm_work_doubles", "srbd_pdipm", "srbd_wrench",
+    "srbd_ctx_create", "srbd_ctx_destroy", "srbd_mpc_solve", "srbd_mpc_solve_host",
+    "srbd_qp_former_evaluate", "srbd_sparse_pdipm_multiple_iterations_evaluate", "srbd_dfma_peak",
+)
+
+
+class SrbdError(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if the .so is absent and nvcc exists).  Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH) and build_if_missing:
+        from . import _build
+        _build.build()
+    if not os.path.exists(LIB_PATH):
+        raise SrbdError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ci, cd, cu = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_uint
+    lib.srbd_version.restype = ci
+    lib.srbd_error_string.restype = ctypes.c_char_p
+    lib.srbd_error_string.argtypes = [ci]
+    lib.srbd_last_cuda_error.restype = ctypes.c_char_p
+    lib.srbd_init.argtypes = [ci]
+    lib.srbd_pattern.argtypes = [ctypes.c_char, ctypes.POINTER(ctypes.POINTER(ci)), ctypes.POINTER(ctypes.POINTER(ci)),
+                                 ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.srbd_qp_form.argtypes = [vp, vp, ci, vp]
+    lib.srbd_pdipm_work_doubles.restype = ctypes.c_size_t
+    lib.srbd_pdipm_work_doubles.argtypes = [ci]
+    lib.srbd_pdipm.argtypes = [vp, vp, vp, vp, ci, ci, cd, cu, vp]
+    lib.srbd_wrench.argtypes = [vp, vp, vp, ci, vp]
+    lib.srbd_ctx_create.argtypes = [ctypes.POINTER(vp), ci, ci]
+    lib.srbd_ctx_destroy.argtypes = [vp]
+    lib.srbd_mpc_solve.argtypes = [vp, vp, vp, ci, ci, ci, cd, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.srbd_mpc_solve_host.argtypes = [vp, vp, vp, ci, ci, ci, cd, vp, vp, vp]
+    lib.srbd_qp_former_evaluate.restype = ctypes.c_float
+    lib.srbd_qp_former_evaluate.argtypes = [vp, vp, vp, ci]
+    lib.srbd_sparse_pdipm_multiple_iterations_evaluate.restype = ctypes.c_float
+    lib.srbd_sparse_pdipm_multiple_iterations_evaluate.argtypes = [vp, vp, vp, ci]
+    lib.srbd_dfma_peak.argtypes = [ci, ci, ci, ctypes.POINTER(cd)]
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        lib = load()
+        msg = lib.srbd_error_string(rc).decode()
+        cuda = lib.srbd_last_cuda_error().decode()
+        raise SrbdError(f"srbd_mpc: {msg} ({rc})" + (f": {cuda}" if cuda else ""))
+
+
+def pattern(which: str):
+    """(colptr, row, nrow, ncol) numpy arrays of the frozen CCS pattern 'H' | 'A' | 'G'."""
+    import numpy as np
+    lib = load()
+    cp = ctypes.POINTER(ctypes.c_int)()
+    rw = ctypes.POINTER(ctypes.c_int)()
+    nrow, ncol, nnz = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(lib.srbd_pattern(which.encode(), ctypes.byref(cp), ctypes.byref(rw), ctypes.byref(nrow),
+                           ctypes.byref(ncol), ctypes.byref(nnz)))
+    colptr = np.ctypeslib.as_array(cp, shape=(ncol.value + 1,)).copy()
+    row = np.ctypeslib.as_array(rw, shape=(nnz.value,)).copy()
+    return colptr, row, nrow.value, ncol.value
+
+
+# ---------------------------------------------------------------------------------------------
+# torch-tensor helpers (device memory + stream plumbing only)
+# ---------------------------------------------------------------------------------------------
+def _ptr_array(tensors: Sequence, allow_none=False):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if (t is None and allow_none) else t.data_ptr()
+    return arr
+
+
+def _stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_inputs(tensors, nnz, B=None, device_type="cuda"):
+    import torch
+    if len(tensors) != len(nnz):
+        raise ValueError(f"expected {len(nnz)} tensors, got {len(tensors)}")
+    out = []
+    for i, (t, n) in enumerate(zip(tensors, nnz)):
+        if t.dtype != torch.float64:
+            raise TypeError(f"argument {i}: expected float64, got {t.dtype}")
+        if t.device.type != device_type:
+            raise ValueError(f"argument {i}: expected a {device_type} tensor")
+        if B is None:
+            B = t.shape[0]
+        if t.numel() != B * n:
+            raise ValueError(f"argument {i}: expected {B}x{n} elements, got shape {tuple(t.shape)}")
+        out.append(t if t.is_contiguous() else t.contiguous())
+    return out, B
+
+
+def qp_form(inputs: Sequence, out: Optional[List] = None) -> List:
+    """qp_former: 17 (B, nnz) fp64 CUDA tensors -> [H, f, A, b, G, d] CCS value tensors."""
+    import torch
+    lib = load()
+    ins, B = _check_inputs(inputs, QP_NNZ_IN)
+    dev = ins[0].device
+    if out is None:
+        out = [torch.empty((B, n), dtype=torch.float64, device=dev) for n in QP_NNZ_OUT]
+    with torch.cuda.device(dev):
+        check(lib.srbd_qp_form(_ptr_array(ins), _ptr_array(out), B, _stream()))
+    return out
+
+
+def pdipm(inputs: Sequence, num_iters: int = 5, tol: float = 0.0, cold_start: bool = False,
+          stage_invariant: bool = False, out: Optional[List] = None, work=None, iters_done=None) -> List:
+    """sparse_pdipm_multiple_iterations with a runtime iteration count.
+    inputs: [Q_val, G_val, A_val, f, h, b, x, s, z, y] (x,s,z,y may be None with cold_start).
+    Returns [x, s, z, y, residuals(B,4), mu(B,1)]."""
+    import torch
+    lib = load()
+    inputs = list(inputs)
+    if cold_start:
+        inputs = inputs[:6] + [None] * 4
+    chk, B = _check_inputs(inputs[:6], IP_NNZ_IN[:6])
+    rest = inputs[6:]
+    if not cold_start:
+        rest, _ = _check_inputs(rest, IP_NNZ_IN[6:], B)
+    ins = chk + list(rest)
+    dev = chk[0].device
+    if out is None:
+        out = [torch.empty((B, n), dtype=torch.float64, device=dev) for n in IP_NNZ_OUT]
+    if work is None:
+        work = torch.empty((B, WORK_DOUBLES), dtype=torch.float64, device=dev)
+    flags = (COLD_START if cold_start else 0) | (STAGE_INVARIANT if stage_invariant else 0)
+    with torch.cuda.device(dev):
+        check(lib.srbd_pdipm(_ptr_array(ins, allow_none=True), _ptr_array(out), ctypes.c_void_p(work.data_ptr()),
+                             ctypes.c_void_p(iters_done.data_ptr()) if iters_done is not None else None,
+                             B, int(num_iters), float(tol), flags, _stream()))
+    return out
+
+
+def wrench(x_sol, rotation_body):
+    import torch
+    lib = load()
+    B = x_sol.shape[0]
+    rot = rotation_body.to(torch.float32).contiguous()
+    out = torch.empty((B, 2, 6), dtype=torch.float32, device=x_sol.device)
+    with torch.cuda.device(x_sol.device):
+        check(lib.srbd_wrench(ctypes.c_void_p(x_sol.data_ptr()), ctypes.c_void_p(rot.data_ptr()),
+                              ctypes.c_void_p(out.data_ptr()), B, _stream()))
+    return out
+
+
+class Context:
+    """Library-owned workspace for the fused tick (srbd_ctx_*)."""
+
+    def __init__(self, max_B: int, device: int = -1):
+        lib = load()
+        self._h = ctypes.c_void_p()
+        check(lib.srbd_ctx_create(ctypes.byref(self._h), int(max_B), int(device)))
+        self.max_B = max_B
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().srbd_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self, inputs17, rotation_body, num_calls=1, iters_per_call=5, tol=0.0, want_iterates=False,
+              iters_done=None):
+        """Device tensors in -> (wrench (B,2,6) fp32[, x, s, z, y, res])."""
+        import torch
+        lib = load()
+        ins, B = _check_inputs(inputs17, QP_NNZ_IN)
+        dev = ins[0].device
+        rot = rotation_body.to(torch.float32).contiguous()
+        w = torch.empty((B, 2, 6), dtype=torch.float32, device=dev)
+        extra = [None] * 5
+        if want_iterates:
+            extra = [torch.empty((B, n), dtype=torch.float64, device=dev) for n in (240, 160, 160, 140, 4)]
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        with torch.cuda.device(dev):
+            check(lib.srbd_mpc_solve(self._h, _ptr_array(ins), ptr(rot), B, int(num_calls), int(iters_per_call),
+                                     float(tol), ptr(w), *[ptr(t) for t in extra], ptr(iters_done), _stream()))
+        return (w, *extra) if want_iterates else w
+
+    def solve_host(self, inputs17_host, rotation_body_host, wrench_host, num_calls=1, iters_per_call=5, tol=0.0,
+                   x_out_host=None, res_out_host=None):
+        """HOST (ideally pinned) tensors in/out; H2D + kernels + D2H; synchronous."""
+        lib = load()
+        B = inputs17_host[0].shape[0]
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        check(lib.srbd_mpc_solve_host(self._h, _ptr_array(inputs17_host), ptr(rotation_body_host), B,
+                                      int(num_calls), int(iters_per_call), float(tol), ptr(wrench_host),
+                                      ptr(x_out_host), ptr(res_out_host)))
+        return wrench_host
+
+
+def dfma_peak(iters=20000, blocks=148 * 8, threads=256) -> float:
+    lib = load()
+    out = ctypes.c_double()
+    check(lib.srbd_dfma_peak(iters, blocks, threads, ctypes.byref(out)))
+    return out.value

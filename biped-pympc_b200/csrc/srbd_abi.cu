@@ -1,0 +1,353 @@
+// C-ABI of the library (declared in include/srbd_mpc.h).  Thin: argument checking, pointer
+// marshalling, stream plumbing, the library-owned workspace of the fused tick and the
+// CusADi-compatible `evaluate` shims.  No algorithmic code lives here.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/srbd_mpc.h"
+#include "srbd_kernels.h"
+
+using namespace srbd;
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e) {
+  std::snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+  return SRBD_ECUDA;
+}
+#define SRBD_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return cuda_fail(e__); } while (0)
+
+const int kQpNnzIn[QP_N_IN] = {12, 120, 120, 120, 1, 1, 1, 9, 9, 3, 3, 3, 20, 12, 12, 3, 3};
+const int kQpNnzOut[QP_N_OUT] = {NNZ_H, NZ, NNZ_A, NEQ, NNZ_G, NINEQ};
+const int kIpNnzIn[IP_N_IN] = {NNZ_H, NNZ_G, NNZ_A, NZ, NINEQ, NEQ, NZ, NINEQ, NINEQ, NEQ};
+const int kIpNnzOut[IP_N_OUT] = {NZ, NINEQ, NINEQ, NEQ, 4, 1};
+
+std::mutex g_init_mu;
+bool g_inited[64] = {false};
+int g_num_sms[64] = {0};
+
+struct Patterns {
+  std::vector<int> h_colptr, h_row, a_colptr, a_row, g_colptr, g_row;
+  Patterns() {
+    for (int j = 0; j <= NZ; ++j) h_colptr.push_back(j);
+    for (int j = 0; j < NZ; ++j) h_row.push_back(j);
+    a_colptr.push_back(0);
+    g_colptr.push_back(0);
+    for (int k = 0; k < N; ++k)
+      for (int c = 0; c < NX; ++c) {         // x_{k+1}[c]
+        a_row.push_back(12 * k + c);
+        if (k < 9)
+          for (int r = 0; r < NX; ++r)
+            if (a_xcol_pos(r, c) >= 0) a_row.push_back(12 * (k + 1) + r);
+        a_colptr.push_back((int)a_row.size());
+        g_colptr.push_back(0);
+      }
+    for (int k = 0; k < N; ++k)
+      for (int c = 0; c < NU; ++c) {         // u_k[c]
+        for (int r = 0; r < NX; ++r)
+          if (a_ucol_pos(r, c) >= 0) a_row.push_back(12 * k + r);
+        if (c == 6) a_row.push_back(120 + 2 * k);
+        if (c == 9) a_row.push_back(121 + 2 * k);
+        a_colptr.push_back((int)a_row.size());
+        for (int ft = 0; ft < 2; ++ft) {
+          const int r0 = 16 * k + 8 * ft;
+          if (c == u_fx(ft)) { g_row.push_back(r0); g_row.push_back(r0 + 1); }
+          if (c == u_fy(ft)) { g_row.push_back(r0 + 2); g_row.push_back(r0 + 3); }
+          if (c == u_fz(ft)) for (int j = 0; j < 8; ++j) g_row.push_back(r0 + j);
+          if (c == u_my(ft)) { g_row.push_back(r0 + 4); g_row.push_back(r0 + 5); }
+        }
+        g_colptr.push_back((int)g_row.size());
+      }
+  }
+};
+const Patterns& patterns() { static Patterns p; return p; }
+
+int ensure_init() {
+  int dev = 0;
+  SRBD_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return SRBD_EINVAL;
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  if (g_inited[dev]) return SRBD_OK;
+  cudaDeviceProp prop;
+  SRBD_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) {
+    std::snprintf(g_cuda_err, sizeof(g_cuda_err), "device %d is sm_%d%d; this library is built for sm_100a only",
+                  dev, prop.major, prop.minor);
+    return SRBD_ENODEV;
+  }
+  g_num_sms[dev] = prop.multiProcessorCount;
+  SRBD_CUDA(qp_form_upload_table());
+  SRBD_CUDA(pdipm_upload_tables());
+  g_inited[dev] = true;
+  return SRBD_OK;
+}
+int num_sms() { int dev = 0; cudaGetDevice(&dev); return g_num_sms[dev] > 0 ? g_num_sms[dev] : 148; }
+
+}  // namespace
+
+struct srbd_ctx {
+  int device = 0;
+  int max_B = 0;
+  double* qp_out[QP_N_OUT] = {nullptr};   // H f A b G d
+  double* it[4] = {nullptr};              // x s z y
+  double* res = nullptr;                  // (B,4)
+  double* mu = nullptr;                   // (B,1)
+  double* work = nullptr;                 // (B, PDIPM_WORK_DOUBLES)
+  double* in_stage[QP_N_IN] = {nullptr};  // device copies of host inputs (host entry only)
+  float* rot_stage = nullptr;
+  float* wrench_stage = nullptr;
+  cudaStream_t stream = nullptr;          // used by the host entry
+};
+
+extern "C" {
+
+int srbd_version(void) { return 100; }
+
+const char* srbd_error_string(int code) {
+  switch (code) {
+    case SRBD_OK: return "ok";
+    case SRBD_EINVAL: return "invalid argument";
+    case SRBD_ECUDA: return "CUDA runtime error (see srbd_last_cuda_error)";
+    case SRBD_ENOMEM: return "out of device memory";
+    case SRBD_ENODEV: return "no usable sm_100 device";
+    default: return "unknown error";
+  }
+}
+const char* srbd_last_cuda_error(void) { return g_cuda_err; }
+
+int srbd_init(int device) {
+  if (device >= 0) SRBD_CUDA(cudaSetDevice(device));
+  return ensure_init();
+}
+
+int srbd_qp_former_nnz_in(int i) { return (i >= 0 && i < QP_N_IN) ? kQpNnzIn[i] : SRBD_EINVAL; }
+int srbd_qp_former_nnz_out(int i) { return (i >= 0 && i < QP_N_OUT) ? kQpNnzOut[i] : SRBD_EINVAL; }
+int srbd_pdipm_nnz_in(int i) { return (i >= 0 && i < IP_N_IN) ? kIpNnzIn[i] : SRBD_EINVAL; }
+int srbd_pdipm_nnz_out(int i) { return (i >= 0 && i < IP_N_OUT) ? kIpNnzOut[i] : SRBD_EINVAL; }
+
+int srbd_pattern(char which, const int** colptr, const int** row, int* nrow, int* ncol, int* nnz) {
+  const Patterns& p = patterns();
+  const std::vector<int>*cp, *rw;
+  int nr;
+  switch (which) {
+    case 'H': cp = &p.h_colptr; rw = &p.h_row; nr = NZ; break;
+    case 'A': cp = &p.a_colptr; rw = &p.a_row; nr = NEQ; break;
+    case 'G': cp = &p.g_colptr; rw = &p.g_row; nr = NINEQ; break;
+    default: return SRBD_EINVAL;
+  }
+  if (colptr) *colptr = cp->data();
+  if (row) *row = rw->data();
+  if (nrow) *nrow = nr;
+  if (ncol) *ncol = NZ;
+  if (nnz) *nnz = (int)rw->size();
+  return SRBD_OK;
+}
+
+int srbd_qp_form(const double* const* in17, double* const* out6, int B, void* stream) {
+  if (!in17 || !out6 || B < 0) return SRBD_EINVAL;
+  if (B == 0) return SRBD_OK;
+  int rc = ensure_init();
+  if (rc) return rc;
+  QpFormArgs a;
+  for (int i = 0; i < QP_N_IN; ++i) { if (!in17[i]) return SRBD_EINVAL; a.in[i] = in17[i]; }
+  for (int i = 0; i < QP_N_OUT; ++i) { if (!out6[i]) return SRBD_EINVAL; a.out[i] = out6[i]; }
+  SRBD_CUDA(launch_qp_form(a, B, num_sms(), (cudaStream_t)stream));
+  return SRBD_OK;
+}
+
+size_t srbd_pdipm_work_doubles(int B) { return B > 0 ? (size_t)B * PDIPM_WORK_DOUBLES : 0; }
+
+int srbd_pdipm(const double* const* in10, double* const* out6, double* work, int* iters_done,
+               int B, int num_iters, double tol, unsigned flags, void* stream) {
+  if (!in10 || !out6 || !work || B < 0 || num_iters < 0) return SRBD_EINVAL;
+  if (B == 0) return SRBD_OK;
+  int rc = ensure_init();
+  if (rc) return rc;
+  PdipmArgs a;
+  const bool cold = (flags & SRBD_COLD_START) != 0;
+  for (int i = 0; i < IP_N_IN; ++i) {
+    if (!in10[i] && !(cold && i >= IP_X)) return SRBD_EINVAL;
+    a.in[i] = in10[i];
+  }
+  for (int i = 0; i < IP_N_OUT; ++i) { if (!out6[i]) return SRBD_EINVAL; a.out[i] = out6[i]; }
+  a.work = work; a.iters_done = iters_done; a.num_iters = num_iters; a.tol = tol; a.cold_start = cold ? 1 : 0;
+  SRBD_CUDA(launch_pdipm(a, B, (flags & SRBD_STAGE_INVARIANT) != 0, num_sms(), (cudaStream_t)stream));
+  return SRBD_OK;
+}
+
+int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, int B, void* stream) {
+  if (!x_sol || !rotation_body || !wrench || B < 0) return SRBD_EINVAL;
+  SRBD_CUDA(launch_wrench(x_sol, rotation_body, wrench, B, (cudaStream_t)stream));
+  return SRBD_OK;
+}
+
+// ---- context -----------------------------------------------------------------------------
+int srbd_ctx_destroy(srbd_ctx* c) {
+  if (!c) return SRBD_OK;
+  cudaSetDevice(c->device);
+  for (auto& p : c->qp_out) cudaFree(p);
+  for (auto& p : c->it) cudaFree(p);
+  cudaFree(c->res); cudaFree(c->mu); cudaFree(c->work);
+  for (auto& p : c->in_stage) cudaFree(p);
+  cudaFree(c->rot_stage); cudaFree(c->wrench_stage);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return SRBD_OK;
+}
+
+int srbd_ctx_create(srbd_ctx** out, int max_B, int device) {
+  if (!out || max_B <= 0) return SRBD_EINVAL;
+  *out = nullptr;
+  int rc = srbd_init(device);
+  if (rc) return rc;
+  srbd_ctx* c = new (std::nothrow) srbd_ctx;
+  if (!c) return SRBD_ENOMEM;
+  cudaGetDevice(&c->device);
+  c->max_B = max_B;
+  const size_t B = (size_t)max_B;
+  bool ok = true;
+  auto alloc = [&](void** p, size_t bytes) { if (ok && cudaMalloc(p, bytes) != cudaSuccess) ok = false; };
+  for (int i = 0; i < QP_N_OUT; ++i) alloc((void**)&c->qp_out[i], B * kQpNnzOut[i] * sizeof(double));
+  const int itn[4] = {NZ, NINEQ, NINEQ, NEQ};
+  for (int i = 0; i < 4; ++i) alloc((void**)&c->it[i], B * itn[i] * sizeof(double));
+  alloc((void**)&c->res, B * 4 * sizeof(double));
+  alloc((void**)&c->mu, B * sizeof(double));
+  alloc((void**)&c->work, B * PDIPM_WORK_DOUBLES * sizeof(double));
+  for (int i = 0; i < QP_N_IN; ++i) alloc((void**)&c->in_stage[i], B * kQpNnzIn[i] * sizeof(double));
+  alloc((void**)&c->rot_stage, B * 9 * sizeof(float));
+  alloc((void**)&c->wrench_stage, B * 12 * sizeof(float));
+  if (ok && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
+  if (!ok) { cudaGetLastError(); srbd_ctx_destroy(c); return SRBD_ENOMEM; }
+  *out = c;
+  return SRBD_OK;
+}
+
+int srbd_mpc_solve(srbd_ctx* c, const double* const* in17, const float* rotation_body, int B,
+                   int num_calls, int iters_per_call, double tol,
+                   float* wrench, double* x_out, double* s_out, double* z_out, double* y_out,
+                   double* res_out, int* iters_done, void* stream) {
+  if (!c || !in17 || B < 0 || B > c->max_B || num_calls < 0 || iters_per_call < 0) return SRBD_EINVAL;
+  if (wrench && !rotation_body) return SRBD_EINVAL;
+  if (B == 0) return SRBD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = srbd_qp_form(in17, c->qp_out, B, st);
+  if (rc) return rc;
+  // the reference chains `num_calls` evaluations of a fixed-iteration kernel, feeding
+  // (x,s,z,y) back (mpc_controller_cusadi.py:144-169); the iterate sequence is identical to
+  // one call with num_calls*iters_per_call iterations, which is what is launched here.
+  double* x = x_out ? x_out : c->it[0];
+  double* s = s_out ? s_out : c->it[1];
+  double* z = z_out ? z_out : c->it[2];
+  double* y = y_out ? y_out : c->it[3];
+  double* res = res_out ? res_out : c->res;
+  const double* in10[IP_N_IN] = {c->qp_out[OUT_H], c->qp_out[OUT_G], c->qp_out[OUT_A], c->qp_out[OUT_F],
+                                 c->qp_out[OUT_D], c->qp_out[OUT_B], nullptr, nullptr, nullptr, nullptr};
+  double* out6[IP_N_OUT] = {x, s, z, y, res, c->mu};
+  rc = srbd_pdipm(in10, out6, c->work, iters_done, B, num_calls * iters_per_call, tol,
+                  SRBD_COLD_START | SRBD_STAGE_INVARIANT, st);
+  if (rc) return rc;
+  if (wrench) return srbd_wrench(x, rotation_body, wrench, B, st);
+  return SRBD_OK;
+}
+
+int srbd_mpc_solve_host(srbd_ctx* c, const double* const* in17_host, const float* rotation_body_host,
+                        int B, int num_calls, int iters_per_call, double tol,
+                        float* wrench_host, double* x_out_host, double* res_out_host) {
+  if (!c || !in17_host || !rotation_body_host || !wrench_host || B < 0 || B > c->max_B) return SRBD_EINVAL;
+  if (B == 0) return SRBD_OK;
+  SRBD_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  for (int i = 0; i < QP_N_IN; ++i) {
+    if (!in17_host[i]) return SRBD_EINVAL;
+    SRBD_CUDA(cudaMemcpyAsync(c->in_stage[i], in17_host[i], (size_t)B * kQpNnzIn[i] * sizeof(double),
+                              cudaMemcpyHostToDevice, st));
+  }
+  SRBD_CUDA(cudaMemcpyAsync(c->rot_stage, rotation_body_host, (size_t)B * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = srbd_mpc_solve(c, c->in_stage, c->rot_stage, B, num_calls, iters_per_call, tol, c->wrench_stage,
+                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+  if (rc) return rc;
+  SRBD_CUDA(cudaMemcpyAsync(wrench_host, c->wrench_stage, (size_t)B * 12 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (x_out_host) SRBD_CUDA(cudaMemcpyAsync(x_out_host, c->it[0], (size_t)B * NZ * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (res_out_host) SRBD_CUDA(cudaMemcpyAsync(res_out_host, c->res, (size_t)B * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SRBD_CUDA(cudaStreamSynchronize(st));
+  return SRBD_OK;
+}
+
+}  // extern "C"
+
+// ---- CusADi-compatible shims ----------------------------------------------------------------
+namespace {
+double* g_compat_work = nullptr;
+size_t g_compat_work_B = 0;
+template <int NIN, int NOUT, class F>
+float compat_eval(const double** inputs, double** outputs, int B, F&& launch) {
+  if (!inputs || !outputs || B < 0) return -1.f;
+  const double* hin[NIN];
+  double* hout[NOUT];
+  if (cudaMemcpy(hin, inputs, sizeof(hin), cudaMemcpyDeviceToHost) != cudaSuccess) return -2.f;
+  if (cudaMemcpy(hout, outputs, sizeof(hout), cudaMemcpyDeviceToHost) != cudaSuccess) return -2.f;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, 0);
+  const int rc = launch(hin, hout);
+  cudaEventRecord(e1, 0);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (rc) return (float)rc;
+  return ms / 1000.f;
+}
+}  // namespace
+
+extern "C" {
+
+float srbd_qp_former_evaluate(const double** inputs, double* /*work*/, double** outputs, int batch_size) {
+  return compat_eval<QP_N_IN, QP_N_OUT>(inputs, outputs, batch_size, [&](const double** hin, double** hout) {
+    return srbd_qp_form(hin, hout, batch_size, nullptr);
+  });
+}
+
+float srbd_sparse_pdipm_multiple_iterations_evaluate(const double** inputs, double* /*work*/, double** outputs,
+                                                      int batch_size) {
+  if ((size_t)batch_size > g_compat_work_B) {
+    cudaFree(g_compat_work);
+    g_compat_work = nullptr; g_compat_work_B = 0;
+    if (cudaMalloc((void**)&g_compat_work, srbd_pdipm_work_doubles(batch_size) * sizeof(double)) != cudaSuccess) return -3.f;
+    g_compat_work_B = (size_t)batch_size;
+  }
+  return compat_eval<IP_N_IN, IP_N_OUT>(inputs, outputs, batch_size, [&](const double** hin, double** hout) {
+    // arbitrary values on the frozen pattern are accepted: no stage-invariance assumption
+    return srbd_pdipm(hin, hout, g_compat_work, nullptr, batch_size, 5, 0.0, 0u, nullptr);
+  });
+}
+
+int srbd_dfma_peak(int iters, int blocks, int threads, double* tflops) {
+  if (!tflops || iters <= 0 || blocks <= 0 || threads <= 0 || threads > 1024) return SRBD_EINVAL;
+  double* sink = nullptr;
+  SRBD_CUDA(cudaMalloc((void**)&sink, sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  launch_dfma_peak(sink, iters / 10 + 1, blocks, threads, nullptr);   // warm-up
+  cudaEventRecord(e0, 0);
+  cudaError_t le = launch_dfma_peak(sink, iters, blocks, threads, nullptr);
+  cudaEventRecord(e1, 0);
+  cudaError_t se = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(sink);
+  if (le != cudaSuccess) return cuda_fail(le);
+  if (se != cudaSuccess) return cuda_fail(se);
+  *tflops = 16.0 * (double)iters * (double)blocks * (double)threads / ((double)ms * 1e-3) / 1e12;
+  return SRBD_OK;
+}
+
+}  // extern "C"

@@ -13,9 +13,10 @@ cudaError_t launch_qp_form(const QpFormArgs& args, int B, int num_sms, cudaStrea
 
 cudaError_t pdipm_upload_tables();
 cudaError_t launch_pdipm(const PdipmArgs& args, int B, bool stage_invariant, int num_sms, cudaStream_t stream);
+int pdipm_warps_per_cta(bool stage_invariant);
 
 // u0 -> body-frame wrench (mpc_controller_cusadi.py:186-203)
-cudaError_t launch_wrench(const double* x_sol, const double* rotation_body_rowmajor, float* wrench,
+cudaError_t launch_wrench(const double* x_sol, const float* rotation_body_rowmajor, float* wrench,
                           int B, cudaStream_t stream);
 // DFMA micro-benchmark used for the FP64 roofline denominator
 cudaError_t launch_dfma_peak(double* sink, int iters, int blocks, int threads, cudaStream_t stream);

@@ -1,0 +1,62 @@
+// Small kernels around the solve: u0 -> body-frame foot wrench (the post-processing of
+// biped_pympc/convex_mpc/mpc_controller_cusadi.py:186-203) and an FP64 FMA throughput
+// micro-benchmark that provides the roofline denominator for the PDIPM kernel.
+#include <cuda_runtime.h>
+
+#include "srbd_kernels.h"
+
+namespace srbd {
+
+// wrench[e] = (2, 6) fp32: [-R' f_L, -R' m_L ; -R' f_R, -R' m_R] with m_x zeroed and the cast to
+// fp32 done *before* the rotation, exactly as the reference does.  R is the row-major
+// state-estimate rotation (B, 3, 3) in fp32.
+__global__ void wrench_kernel(const double* __restrict__ x_sol, const float* __restrict__ rot,
+                              float* __restrict__ wrench, int B) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B) return;
+  const double* u0 = x_sol + (long long)e * NZ + NX * N;
+  float R[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = rot[(long long)e * 9 + i];
+  float v[4][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    v[0][i] = (float)u0[i];        // f_L
+    v[1][i] = (float)u0[6 + i];    // m_L
+    v[2][i] = (float)u0[3 + i];    // f_R
+    v[3][i] = (float)u0[9 + i];    // m_R
+  }
+  v[1][0] = 0.f;
+  v[3][0] = 0.f;
+  float* o = wrench + (long long)e * 12;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)   // (R' v)_i = sum_j R[j][i] v_j
+      o[3 * q + i] = -(R[0 + i] * v[q][0] + R[3 + i] * v[q][1] + R[6 + i] * v[q][2]);
+}
+
+cudaError_t launch_wrench(const double* x_sol, const float* rot, float* wrench, int B, cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  wrench_kernel<<<(B + 127) / 128, 128, 0, stream>>>(x_sol, rot, wrench, B);
+  return cudaGetLastError();
+}
+
+// 8 independent DFMA chains per thread; 16 flop per inner iteration per thread.
+__global__ void dfma_peak_kernel(double* sink, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 123.456) sink[0] = s;   // never true; keeps the chains alive
+}
+
+cudaError_t launch_dfma_peak(double* sink, int iters, int blocks, int threads, cudaStream_t stream) {
+  dfma_peak_kernel<<<blocks, threads, 0, stream>>>(sink, iters);
+  return cudaGetLastError();
+}
+
+}  // namespace srbd

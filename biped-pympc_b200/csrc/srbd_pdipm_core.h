@@ -673,7 +673,8 @@ struct PdipmWarp {
       SRBD_TRACE("rho_aff", vy, 140);
       solve_thomas();
       // ======================= affine recovery + step lengths ============================
-      double mn_s = 1.0, mn_z = 1.0;
+      // min over ALL 160 candidates (1.0 where the direction is non-negative): may exceed 1
+      double mn_s = 1e300, mn_z = 1e300;
       for (int t = 0; t < 5; ++t) {
         const int k = h ? 9 - t : t;
         stage(k);
@@ -734,7 +735,7 @@ struct PdipmWarp {
       }
       solve_thomas();
       // ======================= corrector recovery, combined direction =====================
-      mn_s = 1.0; mn_z = 1.0;
+      mn_s = 1e300; mn_z = 1e300;
       for (int t = 0; t < 5; ++t) {
         const int k = h ? 9 - t : t;
         stage(k);
@@ -750,6 +751,13 @@ struct PdipmWarp {
       w.sync();
       const double a_pri = step_len(warp_min(mn_s));
       const double a_dual = step_len(warp_min(mn_z));
+#ifdef SRBD_HOST_EMUL
+      { double dbg[8] = {a_pri_aff, a_dual_aff, sigma, mu, a_pri, a_dual, mu_aff, 0.0}; SRBD_TRACE("scalars", dbg, 8); }
+      SRBD_TRACE("dx_cor", vx, 240);
+      SRBD_TRACE("dy_cor", vy, 140);
+      SRBD_TRACE("ds_tot", sm + SM::OFF_DG, 160);
+      SRBD_TRACE("dz_tot", sm + SM::OFF_R2, 160);
+#endif
       // ======================= update ====================================================
       double a_new = 0.0;
       for (int i = lane; i < NZ; i += 32) oX[i] = oX[i] + a_pri * (wdx[i] + vx[i]);

@@ -1,0 +1,109 @@
+"""Host glue of the GPU MPC back-end: the B200 counterpart of
+``MPCControllerCusadi`` (biped_pympc/convex_mpc/mpc_controller_cusadi.py:15-205).
+
+``MPCControllerB200.run()`` takes and returns exactly what the reference's ``run()`` does
+(``foot_wrench (B,2,6) fp32, cost (B,)``) and consumes the same controller attributes
+(``x0, x_ref, R_body, contact_table, dt_mpc, mass, mu, Q, R, residual_*_accel`` and
+``state_estimate_data.{rotation_body, root_position, foot_position}`` prepared by
+``BaseMPCController``, base_controller.py:61-257), so ``BipedController`` only needs a new
+key in its solver switch (biped_controller.py:36-45).  It is written as a mixin-style class
+with no dependency on the reference package (which cannot be imported without CasADi).
+
+Marshalling follows mpc_controller_cusadi.py:54-95 including its flattening quirks
+(SURVEY.md 8b): ``R_body`` and the ``(B,10,2)`` contact table are flattened row-major into
+buffers the kernel reads in CasADi column-major order (Q1, Q2).  ``fix_layout=True`` passes
+the mathematically intended layout instead.  Q3 (13-long ``Q`` strided by 12) is *not*
+reproduced by default: ``Q[:12]`` is used for every env; ``reproduce_q_stride_bug=True``
+restores the reference's behaviour bit for bit.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+from . import _native
+
+
+def marshal_inputs(ctrl, fix_layout: bool = False, reproduce_q_stride_bug: bool = False):
+    """The 17 fp64 (B, nnz) tensors of mpc_controller_cusadi.py:77-95 from controller state."""
+    import torch
+    B, dev, Hn = ctrl.num_envs, ctrl.device, ctrl.horizon_length
+    sed = ctrl.state_estimate_data
+    f64 = torch.float64
+    x0 = ctrl.x0.to(f64).contiguous()
+    ones = torch.ones(B, 12 * Hn, device=dev, dtype=f64)
+    x_ref = ctrl.x_ref.contiguous().view(B, -1).to(f64)
+    Rb = ctrl.R_body[:, 0, :, :]
+    rot = sed.rotation_body
+    I_w = rot @ ctrl.biped.I_body.unsqueeze(0) @ rot.transpose(1, 2)
+    contact = ctrl.contact_table
+    if fix_layout:
+        Rb = Rb.transpose(1, 2)           # column-major nnz order of the true R_body
+        I_w = I_w.transpose(1, 2)
+        contact = contact.transpose(1, 2)  # (B,2,10): flat[k] = contact[k % 10, k // 10]
+    Rb = Rb.contiguous().view(B, -1).to(f64)
+    I_w = I_w.contiguous().view(B, -1).to(f64)
+    contact = contact.contiguous().view(B, -1).to(f64)
+    Q = ctrl.Q.to(f64)
+    if reproduce_q_stride_bug and Q.numel() != 12:
+        Qb = Q.unsqueeze(0).repeat(B, 1).reshape(-1)[:B * 12].view(B, 12)   # env e reads Qflat[12e:12e+12]
+    else:
+        Qb = Q[:12].unsqueeze(0).repeat(B, 1)
+    Rw = ctrl.R.to(f64).unsqueeze(0).repeat(B, 1)
+    scalar = lambda v: torch.as_tensor(v, device=dev, dtype=f64) * torch.ones(B, 1, device=dev, dtype=f64)
+    return [
+        x0, ones, ones.clone(), x_ref, ctrl.dt_mpc.to(f64).reshape(B, 1), scalar(ctrl.mass), scalar(ctrl.mu),
+        Rb, I_w, sed.root_position.to(f64).contiguous(), sed.foot_position[:, 0, :].to(f64).contiguous(),
+        sed.foot_position[:, 1, :].to(f64).contiguous(), contact, Qb.contiguous(), Rw.contiguous(),
+        ctrl.residual_lin_accel.to(f64).contiguous(), ctrl.residual_ang_accel.to(f64).contiguous(),
+    ]
+
+
+def solve_tick(inputs17, rotation_body, num_calls: int = 4, iters_per_call: int = 5, tol: float = 0.0,
+               ctx: "_native.Context" = None, want_iterates: bool = False):
+    """form -> cold start -> num_calls x iters_per_call Newton iterations -> body wrench,
+    entirely on the device (mpc_controller_cusadi.py:97-203)."""
+    own = ctx is None
+    if own:
+        ctx = _native.Context(inputs17[0].shape[0], inputs17[0].device.index or 0)
+    try:
+        return ctx.solve(inputs17, rotation_body, num_calls, iters_per_call, tol, want_iterates)
+    finally:
+        if own:
+            import torch
+            torch.cuda.current_stream().synchronize()
+            ctx.close()
+
+
+class MPCControllerB200:
+    """Mixin with the ``init_solver`` / ``run`` pair of the reference's MPC back-ends.
+
+    Use as ``class MPCControllerB200(MPCControllerB200Mixin, BaseMPCController)`` inside the
+    reference package or stand-alone by providing the attributes listed in
+    the module docstring."""
+
+    MAX_ITER = 4          # calls per tick, mpc_controller_cusadi.py:144
+    ITERS_PER_CALL = 5    # generate_solver_function.py:106
+    fix_layout = False
+    reproduce_q_stride_bug = False
+    tol = 0.0
+
+    def init_solver(self):
+        _native.load()
+        dev_index = getattr(self.device, "index", None)
+        if dev_index is None:
+            import torch
+            dev_index = torch.device(self.device).index or 0
+        self._ctx = _native.Context(self.num_envs, dev_index)
+        return self._ctx
+
+    def run(self) -> Tuple["torch.Tensor", "torch.Tensor"]:
+        import torch
+        for hook in ("compute_knot_points", "compute_horizon_state", "set_initial_state", "compute_reference_trajectory"):
+            fn = getattr(self, hook, None)
+            if fn is not None:
+                fn()
+        inputs = marshal_inputs(self, self.fix_layout, self.reproduce_q_stride_bug)
+        foot_wrench = self._ctx.solve(inputs, self.state_estimate_data.rotation_body,
+                                      self.MAX_ITER, self.ITERS_PER_CALL, self.tol)
+        cost = torch.zeros(self.num_envs, device=self.device)   # reference hard-wires 0 (:185)
+        return foot_wrench, cost

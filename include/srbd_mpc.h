@@ -1,0 +1,137 @@
+/* srbd_mpc.h -- C ABI of the B200-native batched SRBD-MPC solve.
+ *
+ * This library replaces, on the hot path of rl-augmented-mpc/Biped-PyMPC, the two
+ * CusADi-generated shared objects
+ *
+ *     libqp_former.so                          ::evaluate
+ *     libsparse_pdipm_multiple_iterations.so   ::evaluate
+ *
+ * that biped_pympc/cusadi/src/CusadiFunction.py:28-46 loads with ctypes and that
+ * biped_pympc/convex_mpc/mpc_controller_cusadi.py:97-169 calls once + four times per MPC
+ * tick.  Every entry point takes plain pointers and sizes (no torch types).
+ *
+ * Tensor convention (identical to the reference, CusadiFunction.py:71-76):
+ *   argument i is a contiguous fp64 device array of shape (B, nnz_i), env-major, element
+ *   order = CasADi nnz order (column-major for dense matrices; CCS order for H, A, G).
+ *
+ *   qp_former (srbd_constraints.py:77-78)
+ *     in  (17): x0[12] x[120] u[120] x_ref[120] dt[1] m[1] mu[1] R_body[9] I_world[9]
+ *               body_pos[3] left_foot_pos[3] right_foot_pos[3] contact_table[20] Q[12] R[12]
+ *               residual_lin_accel[3] residual_ang_accel[3]
+ *     out  (6): H[240] f[240] A[1196] b[140] G[280] d[160]
+ *   sparse_pdipm_multiple_iterations (sparse_pdipm_solver.py:532-534)
+ *     in  (10): Q_val[240] G_val[280] A_val[1196] f[240] h[160] b[140] x[240] s[160] z[160] y[140]
+ *     out  (6): x[240] s[160] z[160] y[140] residuals[4] mu[1]
+ *
+ * All functions return 0 on success or a negative SRBD_E* code; none of them calls exit().
+ * Kernels are launched asynchronously on the caller's stream (a cudaStream_t passed as
+ * void*; NULL = legacy default stream) unless stated otherwise.  The functions are
+ * re-entrant given distinct buffers; call srbd_init() once per device first.
+ */
+#ifndef SRBD_MPC_H_
+#define SRBD_MPC_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRBD_OK 0
+#define SRBD_EINVAL (-1)    /* null pointer / bad size                                  */
+#define SRBD_ECUDA (-2)     /* a CUDA runtime call failed: see srbd_last_cuda_error()   */
+#define SRBD_ENOMEM (-3)    /* context workspace allocation failed                      */
+#define SRBD_ENODEV (-4)    /* no CUDA device / not an sm_100 device                    */
+
+/* flags for srbd_pdipm / srbd_mpc_solve */
+#define SRBD_COLD_START 1u        /* start from x=0, s=max(h,1), z=1, y=1
+                                     (mpc_controller_cusadi.py:138-141); in[x,s,z,y] ignored  */
+#define SRBD_STAGE_INVARIANT 2u   /* caller guarantees Q/G/A values are identical for every
+                                     horizon stage (true for anything qp_former produced);
+                                     selects the shared-memory-resident fast path           */
+
+#define SRBD_NZ 240
+#define SRBD_NEQ 140
+#define SRBD_NINEQ 160
+#define SRBD_NNZ_H 240
+#define SRBD_NNZ_A 1196
+#define SRBD_NNZ_G 280
+#define SRBD_QP_N_IN 17
+#define SRBD_QP_N_OUT 6
+#define SRBD_IP_N_IN 10
+#define SRBD_IP_N_OUT 6
+
+int srbd_version(void);
+const char* srbd_error_string(int code);
+/* text of the last CUDA error seen by this thread ("" if none) */
+const char* srbd_last_cuda_error(void);
+
+/* Upload the pattern tables to `device` (-1 = current device).  Idempotent. */
+int srbd_init(int device);
+
+/* nnz per argument, for binding code that wants to size buffers generically */
+int srbd_qp_former_nnz_in(int i);
+int srbd_qp_former_nnz_out(int i);
+int srbd_pdipm_nnz_in(int i);
+int srbd_pdipm_nnz_out(int i);
+/* CCS patterns (host arrays, library-owned): colptr has ncol+1 entries */
+int srbd_pattern(char which /* 'H','A','G' */, const int** colptr, const int** row, int* nrow, int* ncol, int* nnz);
+
+/* ---- native entry points: HOST arrays of DEVICE pointers ------------------------------ */
+
+/* replaces libqp_former.so::evaluate (generateCUDACode.py:160-183) */
+int srbd_qp_form(const double* const* in17, double* const* out6, int B, void* stream);
+
+/* scratch doubles the caller must provide to srbd_pdipm for B environments */
+size_t srbd_pdipm_work_doubles(int B);
+
+/* replaces libsparse_pdipm_multiple_iterations.so::evaluate; the iteration count is a
+ * runtime argument (the reference bakes num_iters=5, generate_solver_function.py:106).
+ *   tol <= 0 : run exactly num_iters Newton iterations
+ *   tol  > 0 : stop an environment once |rx|,|rs|,|re| (of that iteration) and the post-step
+ *              mu are all < tol (generate_solver_function.py:187), at most num_iters
+ *   iters_done : optional device int[B], iterations executed per environment
+ * in10[6..9] may alias out6[0..3] (in-place continuation of a previous call). */
+int srbd_pdipm(const double* const* in10, double* const* out6, double* work, int* iters_done,
+               int B, int num_iters, double tol, unsigned flags, void* stream);
+
+/* u0 = x[120:132] -> body-frame wrench (B,2,6) fp32, mpc_controller_cusadi.py:186-203.
+ * rotation_body: device fp32 (B,3,3) row-major. */
+int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, int B, void* stream);
+
+/* ---- fused MPC tick with a library-owned workspace ------------------------------------ */
+typedef struct srbd_ctx srbd_ctx;
+int srbd_ctx_create(srbd_ctx** ctx, int max_B, int device);
+int srbd_ctx_destroy(srbd_ctx* ctx);
+/* form -> cold start -> num_calls x iters_per_call Newton iterations -> wrench, device
+ * buffers in / out (mpc_controller_cusadi.py:97-203 without the host round trips).
+ *   x_out/s_out/z_out/y_out/res_out: optional device buffers (NULL = not wanted)        */
+int srbd_mpc_solve(srbd_ctx* ctx, const double* const* in17, const float* rotation_body, int B,
+                   int num_calls, int iters_per_call, double tol,
+                   float* wrench, double* x_out, double* s_out, double* z_out, double* y_out,
+                   double* res_out, int* iters_done, void* stream);
+/* the same with HOST buffers (pinned or pageable): copies the 17 inputs + rotation in, runs,
+ * copies the wrench (and, when not NULL, x_out and res_out) back, and synchronises. */
+int srbd_mpc_solve_host(srbd_ctx* ctx, const double* const* in17_host, const float* rotation_body_host,
+                        int B, int num_calls, int iters_per_call, double tol,
+                        float* wrench_host, double* x_out_host, double* res_out_host);
+
+/* ---- CusADi-compatible entry points (drop-in for CusadiFunction.py:43) ---------------- *
+ * Same signature and pointer convention as the generated `evaluate`: `inputs`/`outputs`  *
+ * are DEVICE arrays of device pointers, `work` is ignored (the kernels keep their        *
+ * scratch in shared memory / an internal buffer), the call runs on the legacy default    *
+ * stream, is synchronous and returns the kernel time in seconds (negative on error).     *
+ * The PDIPM variant performs the reference's fixed 5 Newton iterations.                  */
+float srbd_qp_former_evaluate(const double** inputs, double* work, double** outputs, int batch_size);
+float srbd_sparse_pdipm_multiple_iterations_evaluate(const double** inputs, double* work, double** outputs,
+                                                      int batch_size);
+
+/* ---- measurement helper ----------------------------------------------------------------*
+ * FP64 FMA micro-benchmark (8 independent chains per thread); returns achieved TFLOP/s    *
+ * through *tflops.  Used by bench.py for the PDIPM roofline denominator.                  */
+int srbd_dfma_peak(int iters, int blocks, int threads, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRBD_MPC_H_ */
