@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Benchmark of the batched SRBD-MPC solve (BASELINE.json metric):
+
+    MPC solves/sec at 4096 envs (form + 5-iteration PDIPM, cold start) per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: oracle restatement
+
+A "step" is one pass of the hot path over one batch of synthetic randomized biped states and
+gait schedules (biped-pympc_b200/workload.py): `qp_former` assembly +
+`sparse_pdipm_multiple_iterations` (5 Newton iterations from the reference cold start) for
+every env of the batch, through the fused C-ABI entry `srbd_mpc_solve`.
+Weak scaling: every rank owns its own 4096-env batch (envs are independent; no collective on
+the solve path), value = envs all ranks solved / max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 4096
+ITERS = 5
+FLOP_PER_ITER = 170e3          # structured count per Newton iteration per env
+BYTES_ASSEMBLY = 21664         # 3 616 B in + 18 048 B out per env
+METRIC = "mpc_solves_per_sec_4096_envs_form_plus_5iter_pdipm"
+UNIT = "solves/s"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            p = [x.strip() for x in l.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(n_envs, iters, steps, warmup, threads, seed=20261018):
+    """Times the CPU restatement of the reference path (oracle/srbd_oracle.c: literal qp_former
+    + full-KKT sparse LDL^T PDIPM, OpenMP over envs) on a bounded sample of the workload."""
+    import biped_pympc_b200 as bp
+    from oracle import c_oracle as co
+    inp, _ = bp.workload.make_batch(n_envs, seed=seed)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        qp = co.qp_former(inp, nthreads=threads)
+        co.pdipm(qp, iters, nthreads=threads)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return n_envs / (sum(times) / len(times)), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 2048
+    value, times = cpu_reference_run(sample, ITERS, args.steps, max(args.warmup, 1), threads)
+    ms = 1e3 * sum(times) / len(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{ENVS_PER_GPU}-env batched SRBD MPC, 5 PDIPM iters, fp64 (BASELINE configs[1])",
+                   "envs_per_step_sample": sample, "iters": ITERS, "horizon": 10},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} envs/step of the same seeded workload; oracle/srbd_oracle.c "
+                                   "(CasADi reference not installable offline: port of qp_former + full-KKT "
+                                   "sparse LDL^T PDIPM, OpenMP over envs)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import biped_pympc_b200 as bp
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.envs
+    inp, rot = bp.workload.make_batch(B, seed=20261018, rank=rank)
+    ins = [torch.as_tensor(a, device=dev) for a in inp]
+    rot_t = torch.as_tensor(rot, dtype=torch.float32, device=dev)
+    ctx = bp.Context(B, local_rank)
+    # L2 flush buffer (> 126 MB L2) written between timed steps
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB
+
+    def step():
+        return ctx.solve(ins, rot_t, num_calls=1, iters_per_call=ITERS)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush.fill_(1.0)           # evict L2 between timed iterations (not timed)
+        a.record()
+        step()
+        b.record()
+    barrier()
+    clocks = sampler.stop()
+    times_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(times_ms)
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI (H2D + kernels + D2H inside the timed region) ----
+    h_in = [torch.as_tensor(a).pin_memory() for a in inp]
+    h_rot = torch.as_tensor(rot, dtype=torch.float32).pin_memory()
+    h_w = torch.empty((B, 2, 6), dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        ctx.solve_host(h_in, h_rot, h_w, num_calls=1, iters_per_call=ITERS)
+    n_e2e = max(10, min(args.steps, 100))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        ctx.solve_host(h_in, h_rot, h_w, num_calls=1, iters_per_call=ITERS)   # synchronous
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * n_e2e / e2e_s
+    h2d = sum(a.numel() * 8 for a in h_in) + h_rot.numel() * 4
+    d2h = h_w.numel() * 4
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{B}-env batched SRBD MPC per GPU, 5 PDIPM iters, fp64, cold start "
+                               "(BASELINE configs[1]); form + solve + wrench via srbd_mpc_solve",
+                   "envs_per_gpu": B, "iters": ITERS, "horizon": 10, "parallelism": f"env-sharded x{world}, no collective",
+                   "l2": "256 MB buffer written between timed iterations (L2 flush)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": n_e2e, "api": "srbd_mpc_solve_host (pinned host buffers)"},
+        "gpu_launches": 3 * args.steps,
+        "clocks": clocks,
+    }
+    ts = sorted(times_ms)
+    line["latency_ms"] = {"p50": ts[len(ts) // 2], "p99": ts[min(len(ts) - 1, int(0.99 * len(ts)))], "max": ts[-1]}
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (PDIPM), timed alone with CUDA events -------------
+        peaks, peak_src = _peaks()
+        qp = bp.qp_form(ins)
+        Hv, f, Av, bvec, Gv, d = qp
+        outs = [torch.empty((B, n), dtype=torch.float64, device=dev) for n in bp._native.IP_NNZ_OUT]
+        work = torch.empty((B, bp._native.WORK_DOUBLES), dtype=torch.float64, device=dev)
+        reps = 20
+        k_ms = []
+        for i in range(reps + 3):
+            flush.fill_(0.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            bp.pdipm([Hv, Gv, Av, f, d, bvec], num_iters=ITERS, cold_start=True, stage_invariant=True, out=outs, work=work)
+            b.record()
+            b.synchronize()
+            if i >= 3:
+                k_ms.append(a.elapsed_time(b))
+        pd_ms = sum(k_ms) / len(k_ms)
+        f_ms = []
+        for i in range(reps + 3):
+            flush.fill_(0.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            bp.qp_form(ins, out=qp)
+            b.record()
+            b.synchronize()
+            if i >= 3:
+                f_ms.append(a.elapsed_time(b))
+        fm_ms = sum(f_ms) / len(f_ms)
+        dfma = max(bp.dfma_peak(), bp.dfma_peak())
+        ach = B * ITERS * FLOP_PER_ITER / (pd_ms * 1e-3) / 1e12
+        line["roofline"] = {"kernel": "pdipm_kernel<stage_invariant>", "bound": "fp64", "achieved": ach, "peak": dfma,
+                            "unit": "TFLOP/s", "frac": ach / dfma, "traffic": None,
+                            "kernel_ms": pd_ms, "share_of_step": pd_ms / (total_ms / args.steps) if world == 1 else None,
+                            "peak_source": "DFMA micro-benchmark measured in this run (srbd_dfma_peak); "
+                                           "MEASURED_PEAKS.json has no FP64 entry",
+                            "algorithmic": f"{FLOP_PER_ITER:.0f} flop/iter/env x {ITERS} iters x {B} envs"}
+        ach_bw = B * BYTES_ASSEMBLY / (fm_ms * 1e-3) / 1e9
+        line["roofline_assembly"] = {"kernel": "qp_form_kernel", "bound": "hbm", "achieved": ach_bw,
+                                     "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                                     "frac": ach_bw / peaks.get("hbm_gbs", 6650.0), "traffic": None,
+                                     "kernel_ms": fm_ms, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)"}
+        # ---- CPU baseline on the box's host cores (bounded sample) -----------------------------
+        if world == 1:
+            threads = os.cpu_count() or 1
+            sample = 2048
+            cpu_val, _ = cpu_reference_run(sample, ITERS, 3, 1, threads)
+            line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{sample} envs x 3 steps of the same workload, oracle/srbd_oracle.c "
+                                              "(full-KKT sparse LDL^T, OpenMP over envs)"}
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,307 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): the CUDA path, called through the
+C-ABI, against the oracle on the same seeded inputs and against the golden fixtures.
+
+Tolerances (north_star): fp64 relative error <= 1e-9 (norm-wise per output vector and env)
+on primal/dual iterates at identical iteration counts; assembly <= 1e-12 relative."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import biped_pympc_b200 as bp  # noqa: E402
+from helpers import rel_err  # noqa: E402
+from oracle import c_oracle as co  # noqa: E402
+
+TOL_IP = 1e-9
+DEV = "cuda:0"
+
+
+def _dev(arrs):
+    return [torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=DEV) for a in arrs]
+
+
+def _np(ts):
+    return [t.detach().cpu().numpy() for t in ts]
+
+
+@pytest.fixture(scope="module")
+def batch64():
+    inp, rot = bp.workload.make_batch(64, seed=4242)
+    nom = bp.workload.nominal_standing_inputs()
+    st, rot_s = bp.workload.make_batch(3, seed=5, standing=True)
+    inp = [np.concatenate([a, b, c], 0) for a, b, c in zip(nom, inp, st)]
+    rot = np.concatenate([np.eye(3)[None], rot, rot_s], 0)
+    return inp, rot
+
+
+def _check_qp(got, ref):
+    names = "HfAbGd"
+    for n, g, r in zip(names, got, ref):
+        scale = max(1.0, np.abs(r).max())
+        if n in "HGd":
+            assert np.array_equal(g, r), f"{n} must be bit exact"
+        elif n == "A":
+            assert np.abs(g - r).max() <= 1e-12 * scale
+            assert np.array_equal(g == 0, r == 0) or np.abs(g - r).max() < 1e-15
+        else:   # b, f: differences of O(1) quantities that cancel -> absolute tolerance
+            assert np.abs(g - r).max() <= 1e-12 * scale, (n, np.abs(g - r).max())
+
+
+def test_qp_form_matches_oracle(batch64):
+    inp, _ = batch64
+    got = _np(bp.qp_form(_dev(inp)))
+    _check_qp(got, co.qp_former(inp))
+
+
+def test_qp_form_golden(golden):
+    inputs = [golden[f"in_{n}"] for n in bp.workload.INPUT_NAMES]
+    got = _np(bp.qp_form(_dev(inputs)))
+    _check_qp(got, [golden[f"qp_{n}"] for n in "HfAbGd"])
+
+
+@pytest.mark.parametrize("B", [1, 3, 13, 130])
+def test_qp_form_ragged_batches(B):
+    inp, _ = bp.workload.make_batch(B, seed=B)
+    outs = bp.qp_form(_dev(inp))
+    _check_qp(_np(outs), co.qp_former(inp))
+
+
+def test_qp_form_empty_batch():
+    empty = [torch.empty((0, n), dtype=torch.float64, device=DEV) for n in bp._native.QP_NNZ_IN]
+    out = bp.qp_form(empty)
+    assert [tuple(o.shape) for o in out] == [(0, n) for n in bp._native.QP_NNZ_OUT]
+
+
+@pytest.mark.parametrize("stage_invariant", [True, False])
+def test_pdipm_5_iters_golden(golden, stage_invariant):
+    qp = [golden[f"qp_{n}"] for n in "HfAbGd"]
+    Hv, f, Av, b, Gv, d = _dev(qp)
+    out = _np(bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=5, cold_start=True, stage_invariant=stage_invariant))
+    for i, n in enumerate(("x", "s", "z", "y")):
+        for e in range(qp[0].shape[0]):
+            assert rel_err(out[i][e], golden[f"ip5_{n}"][e]) < TOL_IP, (n, e)
+    assert rel_err(out[4], golden["ip5_res"]) < 1e-8
+    assert rel_err(out[5], golden["ip5_mu"]) < 1e-8
+
+
+@pytest.mark.parametrize("iters", [1, 5])
+def test_pdipm_matches_long_double_oracle(batch64, iters):
+    inp, _ = batch64
+    qp = co.qp_former(inp)
+    ref = co.pdipm(qp, iters, long_double=True)
+    Hv, f, Av, b, Gv, d = _dev(qp)
+    out = _np(bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=iters, cold_start=True, stage_invariant=True))
+    worst = 0.0
+    for i in range(4):
+        for e in range(qp[0].shape[0]):
+            worst = max(worst, rel_err(out[i][e], ref[i][e]))
+    assert worst < TOL_IP, worst
+
+
+def test_pdipm_explicit_start_and_continuation(batch64):
+    """10 inputs given explicitly (no cold-start flag) and 5+5 == 10 bit for bit."""
+    inp, _ = batch64
+    qp = co.qp_former([a[:16] for a in inp])
+    Hv, f, Av, b, Gv, d = _dev(qp)
+    B = 16
+    x = torch.zeros(B, 240, dtype=torch.float64, device=DEV)
+    s = torch.maximum(d, torch.ones_like(d)); z = torch.ones_like(d); y = torch.ones(B, 140, dtype=torch.float64, device=DEV)
+    a = bp.pdipm([Hv, Gv, Av, f, d, b, x, s, z, y], num_iters=5, stage_invariant=True)
+    c = bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=5, cold_start=True, stage_invariant=True)
+    for u, v in zip(a, c):
+        assert torch.equal(u, v)
+    a2 = bp.pdipm([Hv, Gv, Av, f, d, b, a[0], a[1], a[2], a[3]], num_iters=5, stage_invariant=True)
+    ten = bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=10, cold_start=True, stage_invariant=True)
+    for u, v in zip(a2, ten):
+        assert torch.equal(u, v)
+
+
+def test_pdipm_general_path_random_values_on_pattern():
+    """The reference's own GPU-vs-CPU check feeds torch.rand to every nonzero
+    (cusadi/run_cusadi_function_test.py:15): stage-varying values on the frozen pattern."""
+    rng = np.random.default_rng(4)
+    B = 9
+    Hv = rng.uniform(0.5, 2.0, (B, 240)); Gv = rng.uniform(-1, 1, (B, 280)); Av = rng.uniform(-1, 1, (B, 1196))
+    f = rng.normal(size=(B, 240)); d = rng.uniform(0.5, 2, (B, 160)); b = rng.normal(size=(B, 140))
+    x = rng.normal(size=(B, 240)); s = rng.uniform(0.5, 2, (B, 160)); z = rng.uniform(0.5, 2, (B, 160)); y = rng.normal(size=(B, 140))
+    ref = co.pdipm([Hv, f, Av, b, Gv, d], 3, x, s, z, y, long_double=True)
+    out = _np(bp.pdipm(_dev([Hv, Gv, Av, f, d, b, x, s, z, y]), num_iters=3, stage_invariant=False))
+    for i in range(4):
+        assert rel_err(out[i], ref[i]) < 1e-8
+
+
+def test_tolerance_mode_and_iteration_counts(batch64):
+    inp, _ = batch64
+    qp = co.qp_former([a[:8] for a in inp])
+    Hv, f, Av, b, Gv, d = _dev(qp)
+    itd = torch.zeros(8, dtype=torch.int32, device=DEV)
+    one = bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=1, cold_start=True, stage_invariant=True)
+    got = bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=30, tol=1e30, cold_start=True, stage_invariant=True, iters_done=itd)
+    assert itd.tolist() == [1] * 8
+    for u, v in zip(one, got):
+        assert torch.equal(u, v)
+    bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=30, tol=1e-8, cold_start=True, stage_invariant=True, iters_done=itd)
+    assert all(1 <= v <= 30 for v in itd.tolist())
+
+
+def test_cusadi_compatible_evaluate(golden):
+    """lib<fn>.so::evaluate with DEVICE arrays of device pointers (CusadiFunction.py:84-92)."""
+    import os
+    libdir = os.path.join(os.path.dirname(bp._native.LIB_PATH))
+    inputs = _dev([golden[f"in_{n}"] for n in bp.workload.INPUT_NAMES])
+    B = inputs[0].shape[0]
+    outs = [torch.zeros((B, n), dtype=torch.float64, device=DEV) for n in bp._native.QP_NNZ_OUT]
+    in_ptrs = torch.tensor([t.data_ptr() for t in inputs], dtype=torch.int64, device=DEV)
+    out_ptrs = torch.tensor([t.data_ptr() for t in outs], dtype=torch.int64, device=DEV)
+    work = torch.zeros((B, 8), dtype=torch.float64, device=DEV)
+    lib = ctypes.CDLL(os.path.join(libdir, "libqp_former.so"))
+    lib.evaluate.restype = ctypes.c_float
+    lib.evaluate.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    t = lib.evaluate(in_ptrs.data_ptr(), work.data_ptr(), out_ptrs.data_ptr(), B)
+    assert t >= 0
+    _check_qp(_np(outs), [golden[f"qp_{n}"] for n in "HfAbGd"])
+    # solver: 5 iterations from the reference cold start
+    Hv, f, Av, b, Gv, d = outs
+    x = torch.zeros(B, 240, dtype=torch.float64, device=DEV)
+    s = torch.maximum(d, torch.ones_like(d)); z = torch.ones_like(d); y = torch.ones(B, 140, dtype=torch.float64, device=DEV)
+    ins2 = [Hv, Gv, Av, f, d, b, x, s, z, y]
+    outs2 = [torch.zeros((B, n), dtype=torch.float64, device=DEV) for n in bp._native.IP_NNZ_OUT]
+    in2 = torch.tensor([t_.data_ptr() for t_ in ins2], dtype=torch.int64, device=DEV)
+    out2 = torch.tensor([t_.data_ptr() for t_ in outs2], dtype=torch.int64, device=DEV)
+    lib2 = ctypes.CDLL(os.path.join(libdir, "libsparse_pdipm_multiple_iterations.so"))
+    lib2.evaluate.restype = ctypes.c_float
+    lib2.evaluate.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    assert lib2.evaluate(in2.data_ptr(), work.data_ptr(), out2.data_ptr(), B) >= 0
+    for i, n in enumerate(("x", "s", "z", "y")):
+        assert rel_err(outs2[i].cpu().numpy(), golden[f"ip5_{n}"]) < TOL_IP
+
+
+def test_b200function_mirrors_cusadifunction(golden):
+    inputs = _dev([golden[f"in_{n}"] for n in bp.workload.INPUT_NAMES])
+    B = inputs[0].shape[0]
+    former = bp.B200Function("qp_former", B)
+    former.evaluate(inputs)
+    A_dense = former.getDenseOutput(2)
+    assert tuple(A_dense.shape) == (B, 140, 240)
+    from oracle import srbd_oracle as so
+    ref = so.dense_from_ccs(golden["qp_A"][1], so.A_COLPTR, so.A_ROW, (140, 240))
+    assert np.abs(A_dense[1].cpu().numpy() - ref).max() < 1e-12
+    f_dense = former.getDenseOutput(1)
+    assert tuple(f_dense.shape) == (B, 240, 1)
+    solver = bp.B200Function("sparse_pdipm_multiple_iterations", B, stage_invariant=True)
+    Hs, fs, As, bs, Gs, ds = former.outputs_sparse
+    x = torch.zeros(B, 240, dtype=torch.float64, device=DEV)
+    s = torch.maximum(ds, torch.ones_like(ds)); z = torch.ones_like(ds); y = torch.ones(B, 140, dtype=torch.float64, device=DEV)
+    for _ in range(4):      # the reference's MAX_ITER loop, mpc_controller_cusadi.py:144-169
+        solver.evaluate([Hs, Gs, As, fs.reshape(B, -1, 1), ds.reshape(B, -1, 1), bs.reshape(B, -1, 1),
+                         x.reshape(B, -1, 1), s.reshape(B, -1, 1), z.reshape(B, -1, 1), y.reshape(B, -1, 1)])
+        x, s, z, y = [solver.getDenseOutput(i).reshape(B, -1).clone() for i in range(4)]
+    assert rel_err(x.cpu().numpy(), golden["ip20_x"]) < 1e-6
+
+
+class _Obj:
+    pass
+
+
+def _fake_controller(B, seed):
+    """The attributes BaseMPCController prepares (base_controller.py:61-257), fp32 like the reference."""
+    inp, rot = bp.workload.make_batch(B, seed=seed)
+    c = bp.MPCControllerB200()
+    c.num_envs, c.device, c.horizon_length = B, torch.device(DEV), 10
+    f32 = lambda a: torch.as_tensor(a, dtype=torch.float32, device=DEV)
+    c.x0 = f32(inp[0]); c.x_ref = f32(inp[3]).view(B, 10, 12)
+    c.R_body = f32(rot).unsqueeze(1).repeat(1, 10, 1, 1)
+    sed = _Obj(); sed.rotation_body = f32(rot); sed.root_position = f32(inp[9])
+    sed.foot_position = torch.stack([f32(inp[10]), f32(inp[11])], 1)
+    c.state_estimate_data = sed
+    c.biped = _Obj(); c.biped.I_body = f32(bp.workload.I_BODY)
+    c.contact_table = f32(inp[12]).view(B, 10, 2)
+    c.dt_mpc = f32(inp[4]).view(B); c.mass, c.mu = 40.0, 1.0
+    c.Q = torch.tensor([150, 150, 250, 100, 100, 250, 1, 1, 5, 10, 10, 1, 1], dtype=torch.float32, device=DEV)
+    c.R = torch.tensor([1e-5] * 6 + [1e-4] * 6, dtype=torch.float32, device=DEV)
+    c.residual_lin_accel = f32(inp[15]); c.residual_ang_accel = f32(inp[16])
+    return c, inp, rot
+
+
+def test_controller_run_matches_oracle_tick():
+    B = 6
+    c, inp, rot = _fake_controller(B, seed=31)
+    c.init_solver()
+    wrench, cost = c.run()
+    assert tuple(wrench.shape) == (B, 2, 6) and wrench.dtype == torch.float32 and tuple(cost.shape) == (B,)
+    # oracle: same marshalling (I_world recomputed in fp32 like the reference does)
+    ins = [t.cpu().numpy() for t in bp.mpc_controller_b200.marshal_inputs(c)]
+    qp = co.qp_former(ins)
+    it = co.pdipm(qp, 20, long_double=True)
+    from oracle import srbd_oracle as so
+    for e in range(B):
+        u0 = it[0][e][120:132]
+        Rt = rot[e].astype(np.float32).T
+        fl, fr, ml, mr = [u0[i:i + 3].astype(np.float32) for i in (0, 3, 6, 9)]
+        ml[0] = 0; mr[0] = 0
+        ref = np.concatenate([-(Rt @ fl), -(Rt @ ml), -(Rt @ fr), -(Rt @ mr)]).reshape(2, 6)
+        got = wrench[e].cpu().numpy()
+        assert np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_fused_tick_equals_two_step_path(batch64):
+    inp, rot = batch64
+    ins = _dev(inp)
+    rot_t = torch.as_tensor(rot, dtype=torch.float32, device=DEV)
+    ctx = bp.Context(len(rot))
+    w, x, s, z, y, res = ctx.solve(ins, rot_t, num_calls=1, iters_per_call=5, want_iterates=True)
+    Hv, f, Av, b, Gv, d = bp.qp_form(ins)
+    out = bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=5, cold_start=True, stage_invariant=True)
+    assert torch.equal(out[0], x) and torch.equal(out[2], z) and torch.equal(out[4], res)
+    assert torch.equal(bp.wrench(x, rot_t), w)
+    # host entry point: pinned host buffers, H2D + kernels + D2H
+    h_in = [torch.as_tensor(a).pin_memory() for a in inp]
+    h_rot = torch.as_tensor(rot, dtype=torch.float32).pin_memory()
+    h_w = torch.empty((len(rot), 2, 6), dtype=torch.float32).pin_memory()
+    ctx.solve_host(h_in, h_rot, h_w, num_calls=1, iters_per_call=5)
+    assert torch.equal(h_w, w.cpu())
+    ctx.close()
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (4096 envs): size-independent properties instead of the oracle."""
+    B = 4096
+    inp, rot = bp.workload.make_batch(B, seed=20261018)
+    ins = _dev(inp)
+    Hv, f, Av, b, Gv, d = bp.qp_form(ins)
+    assert torch.equal(Hv[:, :12], ins[13]) and torch.equal(Hv[:, 228:], ins[14])
+    dd = d.view(B, 10, 16)
+    ct = ins[12].view(B, 2, 10).transpose(1, 2)                 # column-major (10,2)
+    assert torch.equal(dd[:, :, 7], 500.0 * ct[:, :, 0]) and torch.equal(dd[:, :, 15], 500.0 * ct[:, :, 1])
+    out5 = bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=5, cold_start=True, stage_invariant=True)
+    again = bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=5, cold_start=True, stage_invariant=True)
+    for u, v in zip(out5, again):
+        assert torch.equal(u, v)                                  # deterministic
+    assert all(torch.isfinite(t).all() for t in out5)
+    assert (out5[1] >= 1e-8).all() and (out5[2] >= 1e-8).all()    # clamps
+    # the residuals reported by iteration 5 are those of the iterate after 4 iterations
+    x4, s4, z4, y4, _, _ = bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=4, cold_start=True, stage_invariant=True)
+    from oracle import srbd_oracle as so
+    idx = torch.as_tensor(so.A_ROW.astype(np.int64) * 240 + so.A_COL, device=DEV)
+    Ad = torch.zeros(B, 140 * 240, dtype=torch.float64, device=DEV); Ad[:, idx] = Av; Ad = Ad.view(B, 140, 240)
+    idg = torch.as_tensor(so.G_ROW.astype(np.int64) * 240 + so.G_COL, device=DEV)
+    Gd = torch.zeros(B, 160 * 240, dtype=torch.float64, device=DEV); Gd[:, idg] = Gv; Gd = Gd.view(B, 160, 240)
+    mv = lambda M, v: torch.bmm(M, v.unsqueeze(2)).squeeze(2)
+    rx = Hv * x4 + f + mv(Gd.transpose(1, 2), z4) + mv(Ad.transpose(1, 2), y4)
+    re = mv(Ad, x4) - b
+    rs = mv(Gd, x4) + s4 - d
+    res = torch.stack([rx.norm(dim=1), rs.norm(dim=1), re.norm(dim=1)], 1)
+    assert ((res - out5[4][:, :3]).abs() <= 1e-9 * (1 + res.abs())).all()
+    mu = (out5[1] * out5[2]).sum(1) / 160
+    assert ((mu - out5[4][:, 3]).abs() <= 1e-12 * (1 + mu.abs())).all()
+    # env results do not depend on batch position / size
+    sub = [t[1000:1013].contiguous() for t in (Hv, Gv, Av, f, d, b)]
+    o13 = bp.pdipm(sub, num_iters=5, cold_start=True, stage_invariant=True)
+    assert torch.equal(o13[0], out5[0][1000:1013])
+    # the general (stage-varying) path gives the same answer to round-off
+    gen = bp.pdipm([t[:256].contiguous() for t in (Hv, Gv, Av, f, d, b)], num_iters=5, cold_start=True, stage_invariant=False)
+    assert rel_err(gen[0].cpu().numpy(), out5[0][:256].cpu().numpy()) < 1e-9
