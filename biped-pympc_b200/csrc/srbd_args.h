@@ -21,6 +21,6 @@ struct PdipmArgs {
   int cold_start;               // 1: ignore in[x,s,z,y]; start from x=0, s=max(h,1), z=1, y=1
                                 //    (mpc_controller_cusadi.py:138-141)
 };
-constexpr int PDIPM_WORK_DOUBLES = 704;   // dx_aff(240) dy_aff(140) ds_aff(160) dz_aff(160) + pad
+constexpr int PDIPM_WORK_DOUBLES = 1344;  // dx,dy,ds,dz (affine) + D, 1/W, D*g, r2 per inequality row
 
 }  // namespace srbd

@@ -78,7 +78,7 @@ def emul_pdipm(qp, iters, x=None, s=None, z=None, y=None, tol=0.0, uniform=True)
            zeros(160) if cold else z, zeros(140) if cold else y]
     ins = [np.ascontiguousarray(a, dtype=np.float64) for a in ins]
     outs = [np.zeros((B, n)) for n in (240, 160, 160, 140, 4, 1)]
-    work = np.zeros((B, 704))
+    work = np.zeros((B, 1344))   # = PDIPM_WORK_DOUBLES (srbd_args.h)
     itd = np.zeros(B, np.int32)
     P = ctypes.POINTER(ctypes.c_double)
     inarr = (P * 10)(*[a.ctypes.data_as(P) for a in ins])
