@@ -775,10 +775,12 @@ struct PdipmWarp {
           build_rho(k);
         }
         if (pass == 0) {
+          SRBD_TRACE("rho_aff", vy, 140);
           factor();
           SRBD_TRACE("P", sm + SM::OFF_P, 780);
         }
         solve_thomas();
+        if (pass == 0) SRBD_TRACE("dyd_aff", vy, 120);
         // ---- recover directions, ratio tests ---------------------------------------------
         mn_s = 1e300; mn_z = 1e300;   // min over ALL 160 candidates (1.0 where dv >= 0): may exceed 1
 #pragma unroll 1

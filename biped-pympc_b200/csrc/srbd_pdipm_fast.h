@@ -1,0 +1,823 @@
+// PDIPM Newton iterations for one environment per warp -- the lean fast path for
+// stage-invariant problem data with unit coefficients on x_{k+1} and on the Mx rows, i.e.
+// for everything the reference's `qp_former` produces (srbd_constraints.py:120-135).
+//
+// Same mathematics as srbd_pdipm_core.h (exact block elimination of the reference KKT of
+// biped_pympc/casadi/sparse_pdipm_solver.py:406-448, twisted block-Thomas over ten 12x12
+// Schur blocks); what differs is where the data lives and how many instructions and
+// shared-memory wavefronts one Newton step costs:
+//
+//   * per-lane registers hold the lane's row and column of Bbar, its coupling rows and the
+//     row of the pivot-block inverse it produced in the previous elimination round;
+//   * pivot blocks are inverted by a symmetric sweep: per pivot one 8-byte store per lane
+//     (all-gather of the pivot column), one warp barrier, six 16-byte broadcast loads and
+//     eleven FMAs;
+//   * the rows of P_k a neighbour round needs are handed over in a 72-double window instead
+//     of being re-gathered from the packed storage;
+//   * the per-inequality-row data (s, z, the two direction slots, D w^-1) is lane-private and
+//     lives in the L2-resident work buffer; only D stays in shared memory;
+//   * 2 066 doubles of shared memory per warp -> 14 warps (environments) per SM.
+//
+// Compiled for the GPU (srbd_pdipm.cu) and, for tests only, for the host under the warp
+// emulator of srbd_warp.h.
+#pragma once
+
+#include "srbd_pdipm_core.h"
+
+namespace srbd {
+
+// ---- stage data (doubles) ---------------------------------------------------------------
+enum : int {
+  FB_B = 0,        // Bbar dense [12][14]
+  FB_AB = 168,     // Abar compact: diag[12] | R[3][3] (rows 0..2, cols 6..8) | pv[3]
+  FB_G = 192,      // G values of a stage [28]
+  FB_HX = 220,     // Q_val of a state block [12]
+  FB_HU = 232,     // Q_val of an input block [12]
+  FB_RAW = 244,    // ---- end of the gathered part; then E[12], Mx[2] are gathered and checked
+  FB_PHX = 244,    // 1 / (hx + beta)
+  FB_DER = 256,    // psi_mz[2], psi_mx'[2], 1/mx_den[2], eps_mx[2]
+  FB_CM = 264,     // 2 x 36 coupling coefficient slots
+  FB_SX = 336,     // A phix A' (state part of S_kk without its diagonal term), packed lower (78)
+  FB_SIZE = 414,
+  FB_NSLOT = FB_RAW + 14
+};
+
+struct FastSmem {
+  static constexpr int OFF_P = 0;          // 10 x 78 packed lower; scratch for iterates in phase A
+  static constexpr int OFF_VX = 780;       // 240  r1~ -> dx
+  static constexpr int OFF_VY = 1020;      // 140  re -> rho -> t -> dy
+  static constexpr int OFF_PSI = 1160;     // 10 x 14
+  static constexpr int OFF_BC = 1300;      // 2 x 24 broadcast scratch per half
+  static constexpr int OFF_TR = 1348;      // 2 x 32: D*g and z of the stage being processed ...
+  static constexpr int OFF_PR = 1348;      // ... or (factor only) 2 x 72 handed-over rows of P
+  static constexpr int OFF_D = 1492;       // 160
+  static constexpr int OFF_FB = 1652;
+  static constexpr int SIZE = OFF_FB + FB_SIZE;   // 2066
+};
+// lane-private per-row scratch in the work buffer
+enum : int { FW_DX = 0, FW_DY = 240, FW_S = 380, FW_Z = 540, FW_Q = 700, FW_END = 860 };
+static_assert(FW_END <= PDIPM_WORK_DOUBLES, "work buffer too small");
+
+// host: gather table of the fast path from the table of srbd_stage_table.h
+inline void build_fast_slots(const StageSlot* sb, StageSlot* fs) {
+  for (int i = 0; i < FB_NSLOT; ++i) { fs[i].kind = ST_ZERO; fs[i].rel = 0; }
+  for (int i = 0; i < 168; ++i) fs[FB_B + i] = sb[SB_B + i];
+  for (int i = 0; i < 24; ++i) fs[FB_AB + i] = sb[SB_AP + i];
+  for (int i = 0; i < 28; ++i) fs[FB_G + i] = sb[SB_G + i];
+  for (int i = 0; i < 12; ++i) fs[FB_HX + i] = sb[SB_HX + i];
+  for (int i = 0; i < 12; ++i) fs[FB_HU + i] = sb[SB_HU + i];
+  for (int i = 0; i < 12; ++i) fs[FB_RAW + i] = sb[SB_E + i];
+  for (int i = 0; i < 2; ++i) fs[FB_RAW + 12 + i] = sb[SB_MX + i];
+}
+
+struct PdipmFast {
+  using SM = FastSmem;
+  Warp w;
+  double* sm;
+  const StageSlot* slots;
+  // Register diet: 14 warps per SM are allocated as 16, i.e. 128 registers per thread.  Only what
+  // the elimination rounds need every time stays in registers; everything else is re-read from
+  // shared memory (short latency) instead of being spilled to local memory (L2 latency: the 28 KB
+  // of L1 left beside 228 KB of shared memory cannot hold the spills of 448 threads).
+  const PdipmArgs* pa;
+  long long e;
+  int lane, h, r, rr;
+  int prow[12];                 // packed offsets of row rr
+  int bs0, bs1;                 // sparse rows of column rr of Bbar
+  double c0[4], c1[4];          // row rr of C = Abar diag(phix)  /  row rr of C'
+  int i0[3], i1[3];             // their off-diagonal column indices
+  double phx_rr;                // 1/(hx + beta) of state rr
+  int goa, gob, ca, cz;         // inequality row r: G(r, ca) = fb[goa], G(r, cz) = fb[gob]
+  int psk, psi_i, psf;          // role of input column rr in Psi: kind, index, foot
+  int doff, moff;               // fb offsets of its constant Psi diagonal / 1/mx_den (or of a zero)
+  int g_row0, g_cnt, g_ofs;     // rows / G values of input column rr
+  enum : int { FB_ZERO = FB_B + 12 };   // a structurally zero slot (pad column of Bbar)
+
+  SRBD_DEV const double* gin(int i, int nnz) const { return pa->in[i] + e * nnz; }
+  SRBD_DEV double* gout(int i, int nnz) const { return pa->out[i] + e * nnz; }
+  SRBD_DEV double* gws() const { return pa->work + e * (long long)PDIPM_WORK_DOUBLES; }
+
+  SRBD_DEV double* P(int k) const { return sm + SM::OFF_P + 78 * k; }
+  SRBD_DEV double* fb() const { return sm + SM::OFF_FB; }
+  SRBD_DEV double* bc() const { return sm + SM::OFF_BC + 24 * h; }
+  SRBD_DEV double* tr() const { return sm + SM::OFF_TR + 32 * h; }
+  SRBD_DEV double* pr(int hh) const { return sm + SM::OFF_PR + 72 * hh; }
+  SRBD_DEV double* psi(int k) const { return sm + SM::OFF_PSI + 14 * k; }
+
+  SRBD_DEV double hsel(double a, double b) const { return h ? b : a; }
+
+  // ------------------------------------------------------------------------------------
+  // one-time set-up: gather the stage data, derive the iteration-invariant quantities
+  // returns nonzero when E or the Mx coefficients are not exactly 1
+  // ------------------------------------------------------------------------------------
+  SRBD_DEV int setup() {
+    double* f = fb();
+    int bad = 0;
+    const double* gQ = gin(IP_Q, NNZ_H); const double* gG = gin(IP_G, NNZ_G); const double* gA = gin(IP_A, NNZ_A);
+    for (int i = lane; i < FB_NSLOT; i += 32) {
+      const StageSlot sl = slots[i];
+      double v = 0.0;
+      switch (sl.kind) {   // stage k = 1 stands for every stage
+        case ST_AU: v = ldg(gA + 336 + 86 + sl.rel); break;
+        case ST_E: v = ldg(gA + a_xcol_start(1, sl.rel)); break;
+        case ST_AXPREV: v = ldg(gA + sl.rel); break;
+        case ST_G: v = ldg(gG + 28 + sl.rel); break;
+        case ST_Q: v = ldg(gQ + 12 + sl.rel); break;
+        default: break;
+      }
+      if (i < FB_RAW) f[i] = v;
+      else if (v != 1.0) bad = 1;
+    }
+    for (int m = 16; m >= 1; m >>= 1) bad |= w.shfl_i(bad, lane ^ m);
+    w.sync();
+    const int q = rr;
+    f[FB_PHX + q] = rcp(f[FB_HX + q] + IP_BETA);
+    if (r < 2) {
+      f[FB_DER + r] = rcp(f[FB_HU + 8 + 3 * r] + IP_BETA);             // mz: plain diagonal
+    } else if (r < 4) {                                                 // mx: with its equality row
+      const int i = r - 2;
+      const double eps = f[FB_HU + 6 + 3 * i] + IP_BETA;
+      const double iden = rcp(1.0 + IP_DELTA * eps);
+      f[FB_DER + 2 + i] = IP_DELTA * iden;
+      f[FB_DER + 4 + i] = iden;
+      f[FB_DER + 6 + i] = eps;
+    }
+    w.sync();
+    // ---- per-lane registers ----------------------------------------------------------
+#pragma unroll
+    for (int m = 0; m < 12; ++m) prow[m] = pk(rr, m);
+    bs0 = 3 + rr % 3; bs1 = 9 + rr % 3;
+    phx_rr = f[FB_PHX + rr];
+    {
+      const double* A = f + FB_AB; const double* ph = f + FB_PHX;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { c0[a] = 0.0; c1[a] = 0.0; }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { i0[a] = q; i1[a] = q; }
+      c0[0] = A[q] * ph[q];
+      c1[0] = A[q] * ph[q];
+      if (q < 3) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { i0[j] = 6 + j; c0[1 + j] = A[12 + 3 * q + j] * ph[6 + j]; }
+      } else if (q < 6) { i0[0] = q + 6; c0[1] = A[21 + q - 3] * ph[q + 6]; }
+      else if (q < 9) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { i1[i] = i; c1[1 + i] = A[12 + 3 * i + (q - 6)] * ph[q]; }
+      } else { i1[0] = q - 6; c1[1] = A[21 + q - 9] * ph[q]; }
+      // 36 static slots per type: [0..11] diagonal, [12..20] rows 0-2 x cols 6-8, [21..23] rows
+      // 3-5 (col r+6), [24..32] rows 6-8 x cols 0-2, [33..35] rows 9-11 (col r-6)
+      double* m0 = f + FB_CM; double* m1 = f + FB_CM + 36;
+      m0[q] = c0[0]; m1[q] = c1[0];
+      if (q < 3) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { m0[12 + 3 * q + j] = c0[1 + j]; m1[12 + 3 * q + j] = 0.0; }
+      } else if (q < 6) { m0[21 + q - 3] = c0[1]; m1[21 + q - 3] = 0.0; }
+      else if (q < 9) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { m0[24 + 3 * (q - 6) + i] = 0.0; m1[24 + 3 * (q - 6) + i] = c1[1 + i]; }
+      } else { m0[33 + q - 9] = 0.0; m1[33 + q - 9] = c1[1]; }
+      // A phix A' (row q, lower part)
+      for (int j = 0; j <= q; ++j) {
+        double acc = c0[0] * PdipmWarp<true>::abar(A, j, q);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) acc += c0[1 + a] * PdipmWarp<true>::abar(A, j, i0[a]);
+        f[FB_SX + pk(q, j)] = acc;
+      }
+    }
+    {   // inequality row r
+      const int ft = r >> 3, jj = r & 7;
+      cz = 3 * ft + 2;
+      gob = FB_G + 12 * ft + 4 + jj;
+      goa = FB_ZERO; ca = cz;
+      if (jj < 4) { goa = FB_G + 12 * ft + jj; ca = 3 * ft + (jj >> 1); }
+      else if (jj < 6) { goa = FB_G + 24 + 2 * ft + jj - 4; ca = 7 + 3 * ft; }
+    }
+    {   // input column rr
+      const int c = rr;
+      psf = (c < 6) ? c / 3 : (c >= 9 ? 1 : 0);
+      doff = FB_ZERO; moff = FB_ZERO; psi_i = 0;
+      if (c < 6) {
+        psi_i = c % 3;
+        if (psi_i == 2) { psk = 1; psi_i = 0; } else psk = 0;
+      } else if (c == 7 || c == 10) { psk = 0; psi_i = 2; }
+      else if (c == 8 || c == 11) { psk = 2; psi_i = (c == 11); doff = FB_DER + psi_i; }
+      else { psk = 3; psi_i = (c == 9); doff = FB_DER + 2 + psi_i; moff = FB_DER + 4 + psi_i; }
+      g_row0 = 0; g_cnt = 0; g_ofs = 0;
+      if (c < 6) {
+        const int ft = c / 3, qq = c % 3;
+        if (qq == 0) { g_row0 = 8 * ft; g_cnt = 2; g_ofs = 12 * ft; }
+        else if (qq == 1) { g_row0 = 8 * ft + 2; g_cnt = 2; g_ofs = 12 * ft + 2; }
+        else { g_row0 = 8 * ft; g_cnt = 8; g_ofs = 12 * ft + 4; }
+      } else if (c == 7 || c == 10) { const int ft = (c == 10); g_row0 = 8 * ft + 4; g_cnt = 2; g_ofs = 24 + 2 * ft; }
+    }
+    w.sync();
+    return bad;
+  }
+
+  // ------------------------------------------------------------------------------------
+  // Psi_k applied to the 12-vector at v (shared memory); returns entry rr
+  // ------------------------------------------------------------------------------------
+  SRBD_DEV double psi_apply(const double* ps, const double* v) const {
+    const double* p = ps + 7 * psf;
+    const int fx = 3 * psf;
+    const double dot = p[3] * v[fx] + p[4] * v[fx + 1] + p[5] * v[7 + fx] - v[fx + 2];
+    const double dg = psk == 0 ? p[psi_i] : fb()[doff];
+    const double q = psk == 0 ? p[3 + psi_i] : (psk == 1 ? -1.0 : 0.0);
+    return dg * v[rr] + q * (p[6] * dot);
+  }
+  // over the rows of input column rr: sum_j G[j,c] a_j and sum_j G[j,c] b_j
+  SRBD_DEV void gather_col(const double* va, const double* vb, double& sa, double& sb_) const {
+    const double* g = fb() + FB_G + g_ofs;
+    double xa = 0.0, xb = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool on = i < g_cnt;
+      const double gv = on ? g[i] : 0.0;
+      const double a = on ? va[g_row0 + i] : 0.0;
+      xa = fma(gv, a, xa);
+      if (vb) { const double b = on ? vb[g_row0 + i] : 0.0; xb = fma(gv, b, xb); }
+    }
+    sa = xa; sb_ = xb;
+  }
+  SRBD_DEV double dot12(const double a[12], const double b[12]) const {
+    double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+    for (int c = 0; c < 12; c += 2) { q0 = fma(a[c], b[c], q0); q1 = fma(a[c + 1], b[c + 1], q1); }
+    return q0 + q1;
+  }
+  // column rr of Bbar times the 12-vector at v (shared memory)
+  SRBD_DEV double bcol_dot(const double* v) const {
+    const double* B = fb() + FB_B + rr;
+    const double q0 = B[0] * v[0] + B[14] * v[1] + B[28] * v[2] + B[14 * bs0] * v[bs0];
+    const double q1 = B[84] * v[6] + B[98] * v[7] + B[112] * v[8] + B[14 * bs1] * v[bs1];
+    return q0 + q1;
+  }
+  // row rr of Bbar times the 12-vector v
+  SRBD_DEV double brow_dot(const double v[12]) const {
+    double Brow[12];
+    ld12(fb() + FB_B + 14 * rr, Brow);
+    return dot12(Brow, v);
+  }
+
+  // ------------------------------------------------------------------------------------
+  // rho_k (into vy) from r1~ (vx) and the equality right-hand sides held in vy;
+  // cor: corrector right-hand side (r1x = r4 = 0: only the input part of r1~ is non-zero)
+  // ------------------------------------------------------------------------------------
+  SRBD_DEV void build_rho(int k, bool cor) const {
+    double* vx = sm + SM::OFF_VX;
+    double* vy = sm + SM::OFF_VY;
+    double* b = bc();
+    {
+      double v = psi_apply(psi(k), vx + 120 + 12 * k);
+      if (!cor) v = fma(fb()[moff], -vy[120 + 2 * k + psi_i], v);    // (1/den) r4_mx
+      b[rr] = v;
+    }
+    w.sync();
+    {
+      double bv[12];
+      ld12(b, bv);
+      double rho = brow_dot(bv);
+      if (!cor) {
+        rho += phx_rr * vx[12 * k + rr] + vy[12 * k + rr];
+        if (k >= 1) {
+          const double* xp = vx + 12 * (k - 1);
+          rho += c0[0] * xp[rr] + c0[1] * xp[i0[0]] + c0[2] * xp[i0[1]] + c0[3] * xp[i0[2]];
+        }
+      }
+      if (r < 12) vy[12 * k + rr] = rho;
+    }
+    w.sync();
+  }
+
+  // ------------------------------------------------------------------------------------
+  // row rr of S_kk into a[12]
+  // ------------------------------------------------------------------------------------
+  SRBD_DEV void form_row(int k, double a[12]) const {
+    const double* f = fb();
+    const double* ps = psi(k);
+    const double* der = f + FB_DER;
+    double* b = bc();
+    double wv[12];
+    double sL, sR;
+    {
+      double Brow[12];
+      ld12(f + FB_B + 14 * rr, Brow);
+      double psv[14];
+      const dbl2* q = reinterpret_cast<const dbl2*>(ps);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) { const dbl2 t = q[i]; psv[2 * i] = t.x; psv[2 * i + 1] = t.y; }
+      const double pL = psv[3] * Brow[0] + psv[4] * Brow[1] + psv[5] * Brow[7] - Brow[2];
+      const double pR = psv[10] * Brow[3] + psv[11] * Brow[4] + psv[12] * Brow[10] - Brow[5];
+      b[rr] = pL; b[12 + rr] = pR;
+      wv[0] = psv[0] * Brow[0]; wv[1] = psv[1] * Brow[1]; wv[2] = 0.0;
+      wv[3] = psv[7] * Brow[3]; wv[4] = psv[8] * Brow[4]; wv[5] = 0.0;
+      wv[6] = der[2] * Brow[6]; wv[7] = psv[2] * Brow[7]; wv[8] = der[0] * Brow[8];
+      wv[9] = der[3] * Brow[9]; wv[10] = psv[9] * Brow[10]; wv[11] = der[1] * Brow[11];
+      sL = psv[6] * pL; sR = psv[13] * pR;
+    }
+    // state part: delta + phix on the diagonal, A phix A' (absent for k = 0: x_0 is a parameter)
+    const double fk = (k == 0) ? 0.0 : 1.0;
+    const double dg = phx_rr + IP_DELTA;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) a[j] = fma(fk, f[FB_SX + prow[j]], (rr == j) ? dg : 0.0);
+    w.sync();
+    {
+      double pl[12];
+      ld12(b, pl);
+#pragma unroll
+      for (int j = 0; j < 12; ++j) a[j] = fma(sL, pl[j], a[j]);
+      ld12(b + 12, pl);
+#pragma unroll
+      for (int j = 0; j < 12; ++j) a[j] = fma(sR, pl[j], a[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      const double* Bj = f + FB_B + 14 * j;
+      if (j < 3 || (j >= 6 && j < 9)) {          // dense rows of Bbar (euler, omega)
+        double bj[12];
+        ld12(Bj, bj);
+        double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 12; c += 2) {
+          if (c != 2) q0 = fma(wv[c], bj[c], q0);
+          if (c + 1 != 5) q1 = fma(wv[c + 1], bj[c + 1], q1);
+        }
+        a[j] += q0 + q1;
+      } else {                                    // position / velocity rows: two entries
+        const int c1_ = (j < 6) ? j - 3 : j - 9, c2_ = c1_ + 3;
+        a[j] = fma(wv[c1_], Bj[c1_], fma(wv[c2_], Bj[c2_], a[j]));
+      }
+    }
+  }
+
+  // n -= M P M' with M the coupling of `type`; own = row rr of P, hand = handed-over rows
+  SRBD_DEV void couple(double n[12], const double own[12], const double* hand, int type) const {
+    const double cv0 = type ? c1[0] : c0[0], cv1 = type ? c1[1] : c0[1];
+    const double cv2 = type ? c1[2] : c0[2], cv3 = type ? c1[3] : c0[3];
+    const int base = type ? 0 : 6;
+    int s1 = (type ? i1[0] : i0[0]) - base, s2 = (type ? i1[1] : i0[1]) - base, s3 = (type ? i1[2] : i0[2]) - base;
+    s1 = s1 < 0 ? 0 : (s1 > 5 ? 5 : s1); s2 = s2 < 0 ? 0 : (s2 > 5 ? 5 : s2); s3 = s3 < 0 ? 0 : (s3 > 5 ? 5 : s3);
+    double U[12];
+    {
+      double t1[12];
+      ld12(hand + 12 * s1, t1);
+#pragma unroll
+      for (int m = 0; m < 12; ++m) U[m] = fma(cv1, t1[m], cv0 * own[m]);
+      ld12(hand + 12 * s2, t1);
+#pragma unroll
+      for (int m = 0; m < 12; ++m) U[m] = fma(cv2, t1[m], U[m]);
+      ld12(hand + 12 * s3, t1);
+#pragma unroll
+      for (int m = 0; m < 12; ++m) U[m] = fma(cv3, t1[m], U[m]);
+    }
+    const double* cm = fb() + FB_CM + 36 * type;
+#pragma unroll
+    for (int cc = 0; cc < 12; ++cc) {
+      double o = U[cc] * cm[cc];
+      if (cc < 3) o += U[6] * cm[12 + 3 * cc] + U[7] * cm[12 + 3 * cc + 1] + U[8] * cm[12 + 3 * cc + 2];
+      else if (cc < 6) o += U[cc + 6] * cm[21 + cc - 3];
+      else if (cc < 9) o += U[0] * cm[24 + 3 * (cc - 6)] + U[1] * cm[24 + 3 * (cc - 6) + 1] + U[2] * cm[24 + 3 * (cc - 6) + 2];
+      else o += U[cc - 6] * cm[33 + cc - 9];
+      n[cc] -= o;
+    }
+  }
+
+  // symmetric sweep on all 12 pivots of the SPD block whose row rr is a[]; returns row rr of its
+  // inverse.  Lane c publishes its entry of pivot column p, which by symmetry is entry c of
+  // pivot row p (one 8-byte store per lane instead of a 96-byte row).  The pivot row is scaled
+  // immediately: keeping it unscaled with a deferred factor costs 100x in the residual
+  // |P S - I| (measured), although the entrywise error is the same.
+  SRBD_DEV void sweep_invert(double a[12]) const {
+    double* b = bc();
+    w.sync();   // the broadcast scratch still holds form_row's exchange
+#pragma unroll
+    for (int p = 0; p < 12; ++p) {
+      double* bp = b + 12 * (p & 1);
+      bp[rr] = a[p];
+      w.sync();
+      double bv[12];
+      ld12(bp, bv);
+      const double di = rcp(bv[p]);
+      const bool piv = (rr == p);
+      const double t = a[p] * di;
+      if (piv) {
+#pragma unroll
+        for (int c = 0; c < 12; ++c) if (c != p) a[c] = bv[c] * di;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 12; ++c) if (c != p) a[c] = fma(-t, bv[c], a[c]);
+      }
+      a[p] = piv ? -di : t;
+    }
+#pragma unroll
+    for (int c = 0; c < 12; ++c) a[c] = -a[c];
+  }
+
+  SRBD_DEV void factor() {
+    // rounds 0..3: top k = t (coupling from k-1) | bottom k = 9-t (coupling from k+1)
+    // round 4: top k = 4 ; bottom idle
+    // round 5: top k = 5 with both couplings (from 4 and from 6)
+    // The own row of the neighbour's inverse is re-read from the packed storage, the three other
+    // rows a lane needs come from the 72-double hand-over window.
+#pragma unroll 1
+    for (int t = 0; t < 6; ++t) {
+      const int k = (t == 5) ? 5 : (h ? 9 - t : t);
+      const bool act = (t < 4) || (h == 0);
+      double n[12];
+      form_row(k, n);
+      if (t > 0) {
+        double o[12];
+        const double* Pn = P((t == 5) ? 4 : (h ? k + 1 : k - 1));
+#pragma unroll
+        for (int c = 0; c < 12; ++c) o[c] = Pn[prow[c]];
+        couple(n, o, pr(h), h);
+      }
+      if (t == 5) {
+        double o[12];
+        const double* P6 = P(6);
+#pragma unroll
+        for (int c = 0; c < 12; ++c) o[c] = P6[prow[c]];
+        couple(n, o, pr(1), 1);
+      }
+      sweep_invert(n);
+      if (act) {
+        double* Pk = P(k);
+#pragma unroll
+        for (int c = 0; c < 12; ++c) if (c <= rr) Pk[prow[c]] = n[c];
+        const int slot = h ? rr : rr - 6;
+        if (slot >= 0 && slot < 6) st12(pr(h) + 12 * slot, n);
+      }
+      w.sync();
+    }
+  }
+
+  // ------------------------------------------------------------------------------------
+  // block-Thomas solve on vy[0..119]  (rho -> t -> dy), twisted
+  // ------------------------------------------------------------------------------------
+  SRBD_DEV double prow_dot(const double* Pm, const double v[12]) const {
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+#pragma unroll
+    for (int m = 0; m < 12; m += 3) {
+      q0 = fma(Pm[prow[m]], v[m], q0); q1 = fma(Pm[prow[m + 1]], v[m + 1], q1); q2 = fma(Pm[prow[m + 2]], v[m + 2], q2);
+    }
+    return q0 + q1 + q2;
+  }
+  SRBD_DEV void solve_thomas() {
+    double* vy = sm + SM::OFF_VY;
+    double* b = bc();
+    // forward: t_k -= M (P_nb t_nb).  t = 4: the bottom half applies C_6' (from 6) to block 5,
+    // t = 5: the top half applies C_5 (from 4)
+#pragma unroll 1
+    for (int t = 1; t < 6; ++t) {
+      int k, nb;
+      if (t < 4) { k = h ? 9 - t : t; nb = h ? k + 1 : k - 1; }
+      else if (t == 4) { k = h ? 5 : 4; nb = h ? 6 : 3; }
+      else { k = 5; nb = 4; }
+      const bool act = (t < 5) || (h == 0);
+      double tv[12];
+      ld12(vy + 12 * nb, tv);
+      b[rr] = prow_dot(P(nb), tv);
+      w.sync();
+      const double cv0 = h ? c1[0] : c0[0], cv1 = h ? c1[1] : c0[1], cv2 = h ? c1[2] : c0[2], cv3 = h ? c1[3] : c0[3];
+      const int j1 = h ? i1[0] : i0[0], j2 = h ? i1[1] : i0[1], j3 = h ? i1[2] : i0[2];
+      const double d = cv0 * b[rr] + cv1 * b[j1] + cv2 * b[j2] + cv3 * b[j3];
+      if (act && r < 12) vy[12 * k + rr] -= d;
+      w.sync();
+    }
+    // backward: dy_5 ; then 4|6 ; 3|7 ; 2|8 ; 1|9 ; 0|-   (top uses C_{k+1}', bottom uses C_k)
+#pragma unroll 1
+    for (int t = 0; t < 6; ++t) {
+      int k = (t == 0) ? 5 : (h ? 5 + t : 5 - t);
+      const bool act = (t == 0) ? (h == 0) : (k <= 9);
+      if (k > 9) k = 9;
+      double tk = vy[12 * k + rr];
+      if (t > 0) {
+        const double* yn = vy + 12 * (h ? k - 1 : k + 1);
+        // top: C_{k+1}' (type 1) ; bottom: C_k (type 0)
+        const double cv0 = h ? c0[0] : c1[0], cv1 = h ? c0[1] : c1[1], cv2 = h ? c0[2] : c1[2], cv3 = h ? c0[3] : c1[3];
+        const int j1 = h ? i0[0] : i1[0], j2 = h ? i0[1] : i1[1], j3 = h ? i0[2] : i1[2];
+        tk -= cv0 * yn[rr] + cv1 * yn[j1] + cv2 * yn[j2] + cv3 * yn[j3];
+      }
+      b[rr] = tk;
+      w.sync();
+      double bv[12];
+      ld12(b, bv);
+      const double dy = prow_dot(P(k), bv);
+      if (act && r < 12) vy[12 * k + rr] = dy;
+      w.sync();
+    }
+  }
+
+  SRBD_DEV double warp_sum(double v) const {
+    for (int m = 16; m >= 1; m >>= 1) v += w.shfl_xor(v, m);
+    return v;
+  }
+  SRBD_DEV double warp_min(double v) const {
+    for (int m = 16; m >= 1; m >>= 1) { const double o = w.shfl_xor(v, m); v = o < v ? o : v; }
+    return v;
+  }
+  SRBD_DEV static double ratio(double v, double dv) { return dv < 0.0 ? -v * rcp(dv) : 1.0; }
+  SRBD_DEV static double step_len(double mn) { return fmax(fmin(1.0, 0.99 * mn), 1e-12); }
+
+  // ------------------------------------------------------------------------------------
+  // the whole call
+  // ------------------------------------------------------------------------------------
+  SRBD_DEV int run(const PdipmArgs& A, long long env) {
+    pa = &A; e = env;
+    lane = w.lane(); h = lane >> 4; r = lane & 15; rr = r < 12 ? r : 11;
+    {
+      double* oX = gout(IPO_X, NZ); double* oS = gout(IPO_S, NINEQ); double* oZ = gout(IPO_Z, NINEQ); double* oY = gout(IPO_Y, NEQ);
+      if (A.cold_start) {
+        const double* gH = gin(IP_H, NINEQ);
+        for (int i = lane; i < NZ; i += 32) oX[i] = 0.0;
+        for (int i = lane; i < NINEQ; i += 32) { oS[i] = fmax(ldg(gH + i), 1.0); oZ[i] = 1.0; }
+        for (int i = lane; i < NEQ; i += 32) oY[i] = 1.0;
+      } else {
+        const double* ix = gin(IP_X, NZ); const double* is = gin(IP_S, NINEQ);
+        const double* iz = gin(IP_Z, NINEQ); const double* iy = gin(IP_Y, NEQ);
+        for (int i = lane; i < NZ; i += 32) oX[i] = ix[i];
+        for (int i = lane; i < NINEQ; i += 32) { oS[i] = is[i]; oZ[i] = iz[i]; }
+        for (int i = lane; i < NEQ; i += 32) oY[i] = iy[i];
+      }
+      if (setup()) {   // not qp_former-shaped data: fail loudly (NaN iterates, iteration count -1)
+        const double nan = __builtin_nan("");
+        for (int i = lane; i < NZ; i += 32) oX[i] = nan;
+        for (int i = lane; i < NINEQ; i += 32) { oS[i] = nan; oZ[i] = nan; }
+        for (int i = lane; i < NEQ; i += 32) oY[i] = nan;
+        if (lane == 0) {
+          double* oRes = gout(IPO_RES, 4);
+          oRes[0] = nan; oRes[1] = nan; oRes[2] = nan; oRes[3] = nan; gout(IPO_MU, 1)[0] = nan;
+          if (A.iters_done) A.iters_done[e] = -1;
+        }
+        return -1;
+      }
+    }
+
+    double* vx = sm + SM::OFF_VX;
+    double* vy = sm + SM::OFF_VY;
+    int it = 0;
+    double n_rx = 0, n_rs = 0, n_re = 0, mu_new = 0;
+#pragma unroll 1
+    for (; it < A.num_iters; ++it) {
+      double mu;
+      phase_a(mu, n_rx, n_rs, n_re);
+
+      // ============ two solves with one factorisation: pass 0 affine, pass 1 corrector ======
+      double smu = 0.0, mn_s = 1e300, mn_z = 1e300;
+#ifdef SRBD_HOST_EMUL
+      double a_pri_aff = 0, a_dual_aff = 0;
+#endif
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+        for (int t = 0; t < 5; ++t) {
+          const int k = h ? 9 - t : t;
+          if (pass == 1) corrector_rhs(k, smu);
+          build_rho(k, pass == 1);
+        }
+        if (pass == 0) {
+          SRBD_TRACE("rho_aff", vy, 140);
+          factor();
+          SRBD_TRACE("P", sm + SM::OFF_P, 780);
+        }
+        solve_thomas();
+        if (pass == 0) SRBD_TRACE("dyd_aff", vy, 120);
+        mn_s = 1e300; mn_z = 1e300;   // min over ALL 160 candidates (1.0 where dv >= 0): may exceed 1
+#pragma unroll 1
+        for (int t = 0; t < 5; ++t) recover(h ? 9 - t : t, pass, mn_s, mn_z);
+        if (pass == 0) {
+          w.sync();
+          double* ws = gws();
+          for (int i = lane; i < NZ; i += 32) ws[FW_DX + i] = vx[i];
+          for (int i = lane; i < NEQ; i += 32) ws[FW_DY + i] = vy[i];
+          SRBD_TRACE("dx_aff", vx, 240);
+          SRBD_TRACE("dy_aff", vy, 140);
+          const double ap = step_len(warp_min(mn_s));
+          const double ad = step_len(warp_min(mn_z));
+#ifdef SRBD_HOST_EMUL
+          a_pri_aff = ap; a_dual_aff = ad;
+#endif
+          const double* oS = gout(IPO_S, NINEQ); const double* oZ = gout(IPO_Z, NINEQ);
+          double a_mu = 0.0;
+#pragma unroll
+          for (int t = 0; t < 5; ++t) {
+            const int j = 16 * (h ? 9 - t : t) + r;
+            a_mu = fma(fma(ap, ws[FW_S + j], oS[j]), fma(ad, ws[FW_Z + j], oZ[j]), a_mu);
+          }
+          const double mu_aff = warp_sum(a_mu) / (double)NINEQ;
+          const double sg = mu_aff * rcp(mu);
+          smu = sg * sg * sg * mu;
+          w.sync();
+        }
+      }
+      const double a_pri = step_len(warp_min(mn_s));
+      const double a_dual = step_len(warp_min(mn_z));
+      w.sync();
+#ifdef SRBD_HOST_EMUL
+      { double dbg[8] = {a_pri_aff, a_dual_aff, smu, mu, a_pri, a_dual, 0.0, 0.0}; SRBD_TRACE("scalars", dbg, 8); }
+      SRBD_TRACE("dx_cor", vx, 240);
+      SRBD_TRACE("dy_cor", vy, 140);
+#endif
+      // ======================= update ====================================================
+      {
+        double* ws = gws();
+        double* oX = gout(IPO_X, NZ); double* oS = gout(IPO_S, NINEQ); double* oZ = gout(IPO_Z, NINEQ); double* oY = gout(IPO_Y, NEQ);
+        double a_new = 0.0;
+        for (int i = lane; i < NZ; i += 32) oX[i] = fma(a_pri, ws[FW_DX + i] + vx[i], oX[i]);
+        for (int i = lane; i < NEQ; i += 32) oY[i] = fma(a_dual, ws[FW_DY + i] + vy[i], oY[i]);
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+          const int j = 16 * (h ? 9 - t : t) + r;
+          const double sn = fmax(fma(a_pri, ws[FW_S + j], oS[j]), 1e-8);
+          const double zn = fmax(fma(a_dual, ws[FW_Z + j], oZ[j]), 1e-8);
+          oS[j] = sn; oZ[j] = zn;
+          a_new = fma(sn, zn, a_new);
+        }
+        mu_new = warp_sum(a_new) / (double)NINEQ;
+      }
+      w.sync();
+      if (A.tol > 0.0 && n_rx < A.tol && n_rs < A.tol && n_re < A.tol && mu_new < A.tol) { ++it; break; }
+    }
+    if (lane == 0) {
+      double* oRes = gout(IPO_RES, 4);
+      oRes[0] = n_rx; oRes[1] = n_rs; oRes[2] = n_re; oRes[3] = mu_new;
+      gout(IPO_MU, 1)[0] = mu_new;
+      if (A.iters_done) A.iters_done[e] = it;
+    }
+    return it;
+  }
+
+  // ======================= phase A: residuals, weights, Psi, r1~ ===========================
+  SRBD_DEV void phase_a(double& mu, double& n_rx, double& n_rs, double& n_re) const {
+    const double* f = fb();
+    double* vx = sm + SM::OFF_VX;
+    double* vy = sm + SM::OFF_VY;
+    double* Dsm = sm + SM::OFF_D;
+    double* sx = sm + SM::OFF_P;         // iterate scratch (phase A only): x | y | (hx + beta) x
+    double* sy = sx + 240; double* xs = sx + 380;
+    double* ws = gws();
+    const double* oS = gout(IPO_S, NINEQ); const double* oZ = gout(IPO_Z, NINEQ);
+    const double* gF = gin(IP_F, NZ); const double* gH = gin(IP_H, NINEQ); const double* gB = gin(IP_B, NEQ);
+    {
+      const double* oX = gout(IPO_X, NZ); const double* oY = gout(IPO_Y, NEQ);
+      int m12 = lane % 12;
+      for (int i = lane; i < NZ; i += 32) {
+        const double v = oX[i];
+        sx[i] = v;
+        if (i < 120) xs[i] = v * (f[FB_HX + m12] + IP_BETA);
+        m12 += 8; if (m12 >= 12) m12 -= 12;
+      }
+      for (int i = lane; i < NEQ; i += 32) sy[i] = oY[i];
+    }
+    w.sync();
+    const int jj = r & 7, ft = r >> 3;
+    const double valid = r < 12 ? 1.0 : 0.0;
+    double a_sz = 0, a_rs = 0, a_rx = 0, a_re = 0;
+#pragma unroll 1
+    for (int t = 0; t < 5; ++t) {
+      const int k = h ? 9 - t : t;
+      const int j = 16 * k + r;
+      const double sv = oS[j], zv = oZ[j], hv = ldg(gH + j);
+      const double fu = ldg(gF + 120 + 12 * k + rr), fxv = ldg(gF + 12 * k + rr), bd = ldg(gB + 12 * k + rr);
+      const double bm = ldg(gB + 120 + 2 * k + (r & 1));
+      const double* u = sx + 120 + 12 * k;
+      double* ps = psi(k);
+      double* trd = tr();
+      {   // inequality row j
+        const double ga = f[goa], gb = f[gob];
+        const double pga = w.shfl_xor(ga, 1), pgb = w.shfl_xor(gb, 1);
+        const double rs = ga * u[ca] + gb * u[cz] + sv - hv;
+        const double si = rcp(sv);
+        const double W = fma(si, zv, IP_DELTA);
+        const double q = rcp(fma(IP_DELTA, W, 1.0));     // D / W
+        const double D = W * q;
+        const double Dg = fma(D, rs, -(q * zv));         // D (r2 / W - r3), r2 = -z, r3 = -rs
+        ws[FW_S + j] = fma(IP_DELTA, Dg, -rs); ws[FW_Z + j] = Dg; ws[FW_Q + j] = q;
+        Dsm[j] = D;
+        trd[r] = Dg; trd[16 + r] = zv;
+        a_sz = fma(sv, zv, a_sz); a_rs = fma(rs, rs, a_rs);
+        // Psi: pairs (0,1)->fx (2,3)->fy (4,5)->my ; (6,7) -> fz only
+        const double pD = w.shfl_xor(D, 1);
+        const double gg = gb * gb * D + pgb * pgb * pD;
+        double contrib = gg, ia = 0.0, tq = 0.0;
+        if (jj < 6) {
+          const double eps_ca = f[FB_HU + ca] + IP_BETA;
+          const double cr = gb * pga - pgb * ga;
+          const double aa = eps_ca + ga * ga * D + pga * pga * pD;
+          const double bb = ga * gb * D + pga * pgb * pD;
+          ia = rcp(aa);
+          tq = bb * ia;
+          contrib = (eps_ca * gg + D * pD * cr * cr) * ia;
+        }
+        if (jj & 1) contrib = 0.0;
+        contrib += w.shfl_xor(contrib, 1);
+        contrib += w.shfl_xor(contrib, 2);
+        contrib += w.shfl_xor(contrib, 4);
+        if (jj < 6 && !(jj & 1)) { ps[7 * ft + (jj >> 1)] = ia; ps[7 * ft + 3 + (jj >> 1)] = tq; }
+        if (jj == 6) ps[7 * ft + 6] = rcp(f[FB_HU + cz] + IP_BETA + contrib);
+      }
+      w.sync();
+      {   // input column rr : rx_u and r1~_u
+        const double* yk = sy + 12 * k;
+        double acc = fma(f[FB_HU + rr], u[rr], fu) + bcol_dot(yk);
+        if (psk == 3) acc += sy[120 + 2 * k + psi_i];
+        double gdg, gz;
+        gather_col(trd, trd + 16, gdg, gz);
+        acc += gz;
+        a_rx = fma(valid * acc, acc, a_rx);
+        vx[120 + 12 * k + rr] = -acc - gdg;
+        // state column rr
+        const double hx_rr = f[FB_HX + rr];
+        double ax = fma(hx_rr, sx[12 * k + rr], fxv) + yk[rr];
+        if (k <= 8) {
+          const double* yn = sy + 12 * (k + 1);
+          ax = fma(hx_rr + IP_BETA, c1[0] * yn[rr] + c1[1] * yn[i1[0]] + c1[2] * yn[i1[1]] + c1[3] * yn[i1[2]], ax);
+        }
+        a_rx = fma(valid * ax, ax, a_rx);
+        vx[12 * k + rr] = -ax;
+        // dynamics row rr
+        double uv[12];
+        ld12(u, uv);
+        double re = sx[12 * k + rr] - bd + brow_dot(uv);
+        if (k >= 1) {
+          const double* xp = xs + 12 * (k - 1);
+          re += c0[0] * xp[rr] + c0[1] * xp[i0[0]] + c0[2] * xp[i0[1]] + c0[3] * xp[i0[2]];
+        }
+        a_re = fma(valid * re, re, a_re);
+        vy[12 * k + rr] = re;
+        if (r >= 12 && r < 14) {   // Mx rows
+          const double rm = u[6 + 3 * (r - 12)] - bm;
+          a_re = fma(rm, rm, a_re);
+          vy[120 + 2 * k + (r - 12)] = rm;
+        }
+      }
+      w.sync();
+    }
+    a_sz = warp_sum(a_sz); a_rs = warp_sum(a_rs); a_rx = warp_sum(a_rx); a_re = warp_sum(a_re);
+    mu = a_sz / (double)NINEQ;
+    n_rx = sqrt(a_rx); n_rs = sqrt(a_rs); n_re = sqrt(a_re);
+  }
+
+  // corrector right-hand side of stage k (sparse_pdipm_solver.py:478-479): r1 = r3 = r4 = 0,
+  // r2 = -(s z + ds_aff dz_aff - sigma mu) / s ; leaves -G' D g in the input part of vx
+  SRBD_DEV void corrector_rhs(int k, double smu) const {
+    double* vx = sm + SM::OFF_VX;
+    double* ws = gws();
+    const double* oS = gout(IPO_S, NINEQ); const double* oZ = gout(IPO_Z, NINEQ);
+    const int j = 16 * k + r;
+    const double sv = oS[j], zv = oZ[j], dsa = ws[FW_S + j], dza = ws[FW_Z + j], q = ws[FW_Q + j];
+    const double r2 = -(rcp(sv) * (sv * zv + dsa * dza - smu));
+    const double Dg = q * r2;
+    ws[FW_S + j] = fma(IP_DELTA, Dg, dsa); ws[FW_Z + j] = dza + Dg;
+    double* trd = tr();
+    trd[r] = Dg;
+    w.sync();
+    double gdg, gz;
+    gather_col(trd, nullptr, gdg, gz);
+    vx[120 + 12 * k + rr] = -gdg;
+    w.sync();
+  }
+
+  // recover dx, du (into vx), dy_mx (into vy) and this lane's ds / dz of inequality row 16k + r
+  SRBD_DEV void recover(int k, int pass, double& mn_s, double& mn_z) const {
+    const double* f = fb();
+    double* vx = sm + SM::OFF_VX;
+    double* vy = sm + SM::OFF_VY;
+    double* ws = gws();
+    const double* oS = gout(IPO_S, NINEQ); const double* oZ = gout(IPO_Z, NINEQ);
+    const int j = 16 * k + r;
+    const double sv = oS[j], zv = oZ[j], sS = ws[FW_S + j], sZ = ws[FW_Z + j];
+    double* b = bc();
+    double* vu = vx + 120 + 12 * k;
+    const double* dyk = vy + 12 * k;
+    b[rr] = vu[rr] - bcol_dot(dyk);
+    w.sync();
+    {
+      double du = psi_apply(psi(k), b);
+      if (psk == 3) {     // Mx: input and its equality multiplier in closed form
+        const double r4 = pass ? 0.0 : -vy[120 + 2 * k + psi_i];
+        const double eps = f[FB_DER + 6 + psi_i], iden = f[moff];
+        du = fma(IP_DELTA, b[rr], r4) * iden;
+        if (r < 12) vy[120 + 2 * k + psi_i] = (b[rr] - eps * r4) * iden;
+      }
+      double wx = (pass ? 0.0 : vx[12 * k + rr]) - dyk[rr];
+      if (k <= 8) {
+        const double* dyn = vy + 12 * (k + 1);
+        wx = fma(-(f[FB_HX + rr] + IP_BETA), c1[0] * dyn[rr] + c1[1] * dyn[i1[0]] + c1[2] * dyn[i1[1]] + c1[3] * dyn[i1[2]], wx);
+      }
+      if (r < 12) { vx[12 * k + rr] = phx_rr * wx; vu[rr] = du; }
+    }
+    w.sync();
+    {
+      const double gdu = f[goa] * vu[ca] + f[gob] * vu[cz];
+      const double Dg = sm[SM::OFF_D + j] * gdu;
+      const double dz = sZ + Dg;
+      const double ds = fma(IP_DELTA, Dg, sS - gdu);
+      ws[FW_S + j] = ds; ws[FW_Z + j] = dz;       // affine (pass 0) / combined (pass 1)
+      mn_s = fmin(mn_s, ratio(sv, ds));
+      mn_z = fmin(mn_z, ratio(zv, dz));
+    }
+  }
+};
+
+}  // namespace srbd

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "srbd_stage_table.h"
+#include "srbd_pdipm_fast.h"
 
 namespace srbd {
 static std::map<std::string, std::vector<double>> g_trace;
@@ -36,10 +37,23 @@ static void run_env(const PdipmArgs& A, long long e, const StageSlot* slots, int
   });
 }
 
+static void run_env_fast(const PdipmArgs& A, long long e, const StageSlot* slots) {
+  std::vector<double> smem(FastSmem::SIZE, 0.0);
+  run_warp([&](int lane) {
+    PdipmFast W;
+    W.w.lane_ = lane;
+    W.sm = smem.data();
+    W.slots = slots;
+    W.run(A, e);
+  });
+}
+
 extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, double* work, int* iters_done,
                                int B, int num_iters, double tol, int cold_start, int uniform, int trace) {
   static StageSlot slots[SB_SIZE];
+  static StageSlot fslots[FB_NSLOT];
   build_stage_slots(slots);
+  build_fast_slots(slots, fslots);
   PdipmArgs A;
   for (int i = 0; i < IP_N_IN; ++i) A.in[i] = in10[i];
   for (int i = 0; i < IP_N_OUT; ++i) A.out[i] = out6[i];
@@ -47,7 +61,8 @@ extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, d
   g_trace_on = trace != 0;
   g_trace.clear();
   for (long long e = 0; e < B; ++e) {
-    if (uniform) run_env<true>(A, e, slots, nullptr);
+    if (uniform == 2) run_env_fast(A, e, fslots);
+    else if (uniform) run_env<true>(A, e, slots, nullptr);
     else run_env<false>(A, e, slots, nullptr);
   }
   return 0;

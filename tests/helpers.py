@@ -68,7 +68,12 @@ def emul_lib():
 
 
 def emul_pdipm(qp, iters, x=None, s=None, z=None, y=None, tol=0.0, uniform=True):
-    """Runs the PDIPM *device code* under the CPU warp emulator.  Returns (outs6, iters_done)."""
+    """Runs the PDIPM *device code* under the CPU warp emulator.  Returns (outs6, iters_done).
+    uniform: False = general kernel (srbd_pdipm_core.h, arbitrary values on the pattern),
+             True / 2 = stage-invariant fast kernel (srbd_pdipm_fast.h),
+             1 = stage-invariant instantiation of the general kernel."""
+    if uniform is True:
+        uniform = 2
     lib = emul_lib()
     Hv, f, Av, b, Gv, d = qp
     B = Hv.shape[0]
