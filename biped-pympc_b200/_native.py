@@ -222,11 +222,13 @@ class Context:
 
     def solve_host(self, inputs17_host, rotation_body_host, wrench_host, num_calls=1, iters_per_call=5, tol=0.0,
                    x_out_host=None, res_out_host=None):
-        """HOST (ideally pinned) tensors in/out; H2D + kernels + D2H; synchronous."""
+        """HOST (ideally pinned) tensors in/out; H2D + kernels + D2H; synchronous.
+        inputs17_host[1] / [2] (x, u: the linearisation point) may be None = all ones, the constant
+        the reference call site uses (mpc_controller_cusadi.py:55-56); they are then not copied."""
         lib = load()
         B = inputs17_host[0].shape[0]
         ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
-        check(lib.srbd_mpc_solve_host(self._h, _ptr_array(inputs17_host), ptr(rotation_body_host), B,
+        check(lib.srbd_mpc_solve_host(self._h, _ptr_array(inputs17_host, allow_none=True), ptr(rotation_body_host), B,
                                       int(num_calls), int(iters_per_call), float(tol), ptr(wrench_host),
                                       ptr(x_out_host), ptr(res_out_host)))
         return wrench_host

@@ -243,20 +243,23 @@ qp_form_kernel(QpFormArgs a, int B) {
     emit(a.out[OUT_B], NEQ, TAB_B);
     emit(a.out[OUT_D], NINEQ, TAB_D);
     {   // f = grad - H z   (srbd_constraints.py:67-69), evaluated literally
-      const double2* x2 = reinterpret_cast<const double2*>(a.in[IN_X] + (long long)env0 * 120);
-      const double2* u2 = reinterpret_cast<const double2*>(a.in[IN_U] + (long long)env0 * 120);
+      // the linearisation point (x, u) only enters through round-off; NULL = all ones, the constant
+      // the reference call site passes (mpc_controller_cusadi.py:55-56)
+      const double2* x2 = a.in[IN_X] ? reinterpret_cast<const double2*>(a.in[IN_X] + (long long)env0 * 120) : nullptr;
+      const double2* u2 = a.in[IN_U] ? reinterpret_cast<const double2*>(a.in[IN_U] + (long long)env0 * 120) : nullptr;
       const double2* r2 = reinterpret_cast<const double2*>(a.in[IN_XREF] + (long long)env0 * 120);
       double2* f2 = reinterpret_cast<double2*>(a.out[OUT_F] + (long long)env0 * NZ);
+      const double2 ones = make_double2(1.0, 1.0);
       for (int i = tid; i < nenv * 120; i += nthr) {
         const int e = i / 120, k = (i - e * 120) * 2;   // k in 0..238 (even)
         double2 v;
         if (k < 120) {
-          const double2 xv = x2[e * 60 + (k >> 1)], rv = r2[e * 60 + (k >> 1)];
+          const double2 xv = x2 ? x2[e * 60 + (k >> 1)] : ones, rv = r2[e * 60 + (k >> 1)];
           const double q0 = sV[e][V_Q + k % 12], q1 = sV[e][V_Q + (k + 1) % 12];
           v.x = q0 * (xv.x - rv.x) - q0 * xv.x;
           v.y = q1 * (xv.y - rv.y) - q1 * xv.y;
         } else {
-          const double2 uv = u2[e * 60 + ((k - 120) >> 1)];
+          const double2 uv = u2 ? u2[e * 60 + ((k - 120) >> 1)] : ones;
           const double r0 = sV[e][V_R + k % 12], r1 = sV[e][V_R + (k + 1) % 12];
           const double t0 = r0 * uv.x, t1 = r1 * uv.y;
           v.x = t0 - t0;

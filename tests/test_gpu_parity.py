@@ -273,6 +273,44 @@ def test_fused_tick_equals_two_step_path(batch64):
     ctx.close()
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_host_entry_chunks_and_default_linearisation_point(pinned):
+    """srbd_mpc_solve_host cuts the batch into chunks on two streams (pinned buffers are read /
+    written in place over PCIe, pageable ones are staged) and accepts NULL for the (dead)
+    linearisation point x, u = ones: all of it must leave the result bit-identical."""
+    B = 2500                                   # 2 (pinned) / 3 (pageable) chunks, the last one ragged
+    inp, rot = bp.workload.make_batch(B, seed=77)
+    ctx = bp.Context(B)
+    rot_t = torch.as_tensor(rot, dtype=torch.float32, device=DEV)
+    w_dev, x_dev = ctx.solve(_dev(inp), rot_t, num_calls=1, iters_per_call=5, want_iterates=True)[:2]
+    pin = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+    h_in = [pin(torch.as_tensor(a)) for a in inp]
+    h_rot = pin(torch.as_tensor(rot, dtype=torch.float32))
+    h_w = pin(torch.empty((B, 2, 6), dtype=torch.float32))
+    h_x = pin(torch.empty((B, 240), dtype=torch.float64))
+    ctx.solve_host(h_in, h_rot, h_w, num_calls=1, iters_per_call=5, x_out_host=h_x)
+    assert torch.equal(h_w, w_dev.cpu()) and torch.equal(h_x, x_dev.cpu())
+    h_in2 = list(h_in); h_in2[1] = None; h_in2[2] = None
+    h_w2 = pin(torch.zeros_like(h_w))
+    h_x2 = pin(torch.zeros_like(h_x))
+    ctx.solve_host(h_in2, h_rot, h_w2, num_calls=1, iters_per_call=5, x_out_host=h_x2)
+    assert torch.equal(h_w2, h_w) and torch.equal(h_x2, h_x)
+    ctx.close()
+
+
+def test_fast_path_rejects_data_that_is_not_qp_former_shaped(golden):
+    """SRBD_STAGE_INVARIANT promises unit coefficients on x_{k+1} / Mx rows; anything else must
+    fail loudly (NaN iterates, iteration count -1), never silently solve another problem."""
+    qp = [golden[f"qp_{n}"] for n in "HfAbGd"]
+    Hv, f, Av, b, Gv, d = _dev(qp)
+    Av = Av.clone(); Av[:, 36] = 2.0     # coefficient of x_2[0] in dyn_1 (a_xcol_start(1, 0), srbd_pattern.h)
+    itd = torch.zeros(Av.shape[0], dtype=torch.int32, device=DEV)
+    out = bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=5, cold_start=True, stage_invariant=True, iters_done=itd)
+    assert torch.isnan(out[0]).all() and (itd == -1).all()
+    gen = bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=5, cold_start=True, stage_invariant=False)
+    assert torch.isfinite(gen[0]).all()
+
+
 def test_full_size_properties():
     """BASELINE config 2 size (4096 envs): size-independent properties instead of the oracle."""
     B = 4096
