@@ -260,8 +260,20 @@ def run_b200(args):
         fm_ms = sum(f_ms) / len(f_ms)
         dfma = max(bp.dfma_peak(), bp.dfma_peak())
         ach = B * ITERS * FLOP_PER_ITER / (pd_ms * 1e-3) / 1e12
-        line["roofline"] = {"kernel": "pdipm_kernel<stage_invariant>", "bound": "fp64", "achieved": ach, "peak": dfma,
-                            "unit": "TFLOP/s", "frac": ach / dfma, "traffic": None,
+        traffic, cap = None, {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_capture.json")) as fcap:
+                cap = json.load(fcap)
+            traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+        except Exception:
+            pass
+        line["roofline"] = {"kernel": "pdipm_fast_kernel<14> (stage-invariant PDIPM, one warp per env)", "bound": "fp64",
+                            "achieved": ach, "peak": dfma,
+                            "unit": "TFLOP/s", "frac": ach / dfma, "traffic": traffic,
+                            "traffic_note": "DRAM bytes per launch from the committed ncu capture "
+                                            f"({cap.get('capture')}); algorithmic I/O is 29 288 B/env = {29288 * B} B: "
+                                            "the kernel is bound by the FP64 pipe and shared-memory bandwidth, not HBM",
+                            "smem_wavefronts_per_sm_cycle_ncu": cap.get("smem_wavefronts_per_sm_cycle"),
                             "kernel_ms": pd_ms, "share_of_step": pd_ms / (total_ms / args.steps) if world == 1 else None,
                             "peak_source": "DFMA micro-benchmark measured in this run (srbd_dfma_peak); "
                                            "MEASURED_PEAKS.json has no FP64 entry",
