@@ -146,7 +146,13 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout at the first collective: keep stdout for the
+        # ONE JSON line by pointing fd 1 at stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     B = args.envs
@@ -157,8 +163,10 @@ def run_b200(args):
     # L2 flush buffer (> 126 MB L2) written between timed steps
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB
 
+    iters_done = torch.zeros(B, dtype=torch.int32, device=dev) if args.tol > 0 else None
+
     def step():
-        return ctx.solve(ins, rot_t, num_calls=1, iters_per_call=ITERS)
+        return ctx.solve(ins, rot_t, num_calls=args.calls, iters_per_call=args.iters, tol=args.tol, iters_done=iters_done)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -197,12 +205,12 @@ def run_b200(args):
     h_rot = torch.as_tensor(rot, dtype=torch.float32).pin_memory()
     h_w = torch.empty((B, 2, 6), dtype=torch.float32).pin_memory()
     for _ in range(3):
-        ctx.solve_host(h_in, h_rot, h_w, num_calls=1, iters_per_call=ITERS)
+        ctx.solve_host(h_in, h_rot, h_w, num_calls=args.calls, iters_per_call=args.iters, tol=args.tol)
     n_e2e = max(10, min(args.steps, 100))
     barrier()
     t0 = time.perf_counter()
     for _ in range(n_e2e):
-        ctx.solve_host(h_in, h_rot, h_w, num_calls=1, iters_per_call=ITERS)   # synchronous
+        ctx.solve_host(h_in, h_rot, h_w, num_calls=args.calls, iters_per_call=args.iters, tol=args.tol)   # synchronous
     e2e_s = time.perf_counter() - t0
     if dist is not None:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -212,13 +220,16 @@ def run_b200(args):
     h2d = sum(a.numel() * 8 for a in h_in if a is not None) + h_rot.numel() * 4
     d2h = h_w.numel() * 4
 
+    default_wl = (args.calls == 1 and args.iters == ITERS and args.tol <= 0)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if default_wl else "mpc_solves_per_sec", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{B}-env batched SRBD MPC per GPU, 5 PDIPM iters, fp64, cold start "
-                               "(BASELINE configs[1]); form + solve + wrench via srbd_mpc_solve",
-                   "envs_per_gpu": B, "iters": ITERS, "horizon": 10, "parallelism": f"env-sharded x{world}, no collective",
+        "config": {"workload": (f"{B}-env batched SRBD MPC per GPU, 5 PDIPM iters, fp64, cold start "
+                                "(BASELINE configs[1]); form + solve + wrench via srbd_mpc_solve") if default_wl else
+                               (f"{B}-env batched SRBD MPC per GPU, {args.calls} x {args.iters} PDIPM iters"
+                                + (f" or tol {args.tol:g}" if args.tol > 0 else "") + ", fp64, cold start; srbd_mpc_solve"),
+                   "envs_per_gpu": B, "iters": args.calls * args.iters, "horizon": 10, "parallelism": f"env-sharded x{world}, no collective",
                    "l2": "256 MB buffer written between timed iterations (L2 flush)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": n_e2e, "api": "srbd_mpc_solve_host (pinned host buffers read and written in place over PCIe by the kernels; two 2058-env chunks on two streams)"},
@@ -228,6 +239,10 @@ def run_b200(args):
     ts = sorted(times_ms)
     line["latency_ms"] = {"p50": ts[len(ts) // 2], "p99": ts[min(len(ts) - 1, int(0.99 * len(ts)))], "max": ts[-1]}
 
+    if iters_done is not None:
+        hist = torch.bincount(iters_done.clamp(min=0).to(torch.int64), minlength=args.calls * args.iters + 1).tolist()
+        line["iterations_histogram"] = {str(i): c for i, c in enumerate(hist) if c}
+    n_it = args.calls * args.iters
     if rank == 0:
         # ---- roofline of the dominant kernel (PDIPM), timed alone with CUDA events -------------
         peaks, peak_src = _peaks()
@@ -241,7 +256,8 @@ def run_b200(args):
             flush.fill_(0.0)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            bp.pdipm([Hv, Gv, Av, f, d, bvec], num_iters=ITERS, cold_start=True, stage_invariant=True, out=outs, work=work)
+            bp.pdipm([Hv, Gv, Av, f, d, bvec], num_iters=n_it, tol=args.tol, cold_start=True, stage_invariant=True, out=outs, work=work,
+                     iters_done=iters_done)
             b.record()
             b.synchronize()
             if i >= 3:
@@ -259,7 +275,8 @@ def run_b200(args):
                 f_ms.append(a.elapsed_time(b))
         fm_ms = sum(f_ms) / len(f_ms)
         dfma = max(bp.dfma_peak(), bp.dfma_peak())
-        ach = B * ITERS * FLOP_PER_ITER / (pd_ms * 1e-3) / 1e12
+        done_iters = float(iters_done.clamp(min=0).sum().item()) if iters_done is not None else float(B * n_it)
+        ach = done_iters * FLOP_PER_ITER / (pd_ms * 1e-3) / 1e12
         traffic, cap = None, {}
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_capture.json")) as fcap:
@@ -277,21 +294,26 @@ def run_b200(args):
                             "kernel_ms": pd_ms, "share_of_step": pd_ms / (total_ms / args.steps) if world == 1 else None,
                             "peak_source": "DFMA micro-benchmark measured in this run (srbd_dfma_peak); "
                                            "MEASURED_PEAKS.json has no FP64 entry",
-                            "algorithmic": f"{FLOP_PER_ITER:.0f} flop/iter/env x {ITERS} iters x {B} envs"}
+                            "algorithmic": f"{FLOP_PER_ITER:.0f} flop/iter/env x {done_iters / B:.2f} iters (mean) x {B} envs"}
         ach_bw = B * BYTES_ASSEMBLY / (fm_ms * 1e-3) / 1e9
         line["roofline_assembly"] = {"kernel": "qp_form_kernel", "bound": "hbm", "achieved": ach_bw,
                                      "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                                      "frac": ach_bw / peaks.get("hbm_gbs", 6650.0), "traffic": None,
                                      "kernel_ms": fm_ms, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)"}
         # ---- CPU baseline on the box's host cores (bounded sample) -----------------------------
-        if world == 1:
+        if world == 1 and default_wl:
             threads = os.cpu_count() or 1
             sample = 2048
             cpu_val, _ = cpu_reference_run(sample, ITERS, 3, 1, threads)
             line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{sample} envs x 3 steps of the same workload, oracle/srbd_oracle.c "
                                               "(full-KKT sparse LDL^T, OpenMP over envs)"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        if saved_stdout is not None:
+            os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        if saved_stdout is not None:
+            os.dup2(2, 1)
     ctx.close()
     if dist is not None:
         dist.barrier()
@@ -305,6 +327,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    # other BASELINE configs (not the default bench line): --calls 4 = the reference tick (4 x 5 iterations,
+    # mpc_controller_cusadi.py:144-169); --envs 16384 --iters 30 --tol 1e-8 = run to convergence (config 4)
+    ap.add_argument("--calls", type=int, default=1, help="chained PDIPM calls per tick")
+    ap.add_argument("--iters", type=int, default=ITERS, help="Newton iterations per call")
+    ap.add_argument("--tol", type=float, default=0.0, help="> 0: stop an env when rx, rs, re, mu < tol")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
