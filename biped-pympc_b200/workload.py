@@ -139,3 +139,17 @@ def nominal_standing_inputs():
     vals = [x0, z[:120], z[120:], x_ref, [dt], [m], [mu], np.eye(3).reshape(9, order="F"),
             I_w.reshape(9, order="F"), body, lf, rf, np.ones(20), Q, R, np.zeros(3), np.zeros(3)]
     return [np.asarray(v, np.float64).reshape(1, -1) for v in vals]
+
+
+def config1_t1_standing():
+    """BASELINE.json configs[0] / SURVEY 8(d) config 1: a single T1 biped (m = 40, mu = 1,
+    t1.py:70-75), dt = 0.025, horizon 10 (configuration.py:38-40), Q / R of configuration.py:45,50,
+    in the standing pose of generate_solver_function.py:26-58 (body z = 0.5, feet (0.1, +-0.05, 0),
+    x0[5] = x_ref[5] = 0.55, identity rotation, zero residuals, all contact), linearisation point
+    x = u = 1 as the controller passes it (mpc_controller_cusadi.py:55-56)."""
+    body = np.array([0.0, 0.0, 0.5]); lf = np.array([0.1, 0.05, 0.0]); rf = np.array([0.1, -0.05, 0.0])
+    x0 = np.zeros(12); x0[5] = 0.55
+    x_ref = np.zeros(120); x_ref[5::12] = 0.55
+    vals = [x0, np.ones(120), np.ones(120), x_ref, [0.025], [MASS_T1], [MU_T1], np.eye(3).reshape(9, order="F"),
+            I_BODY.reshape(9, order="F"), body, lf, rf, np.ones(20), Q_DEFAULT, R_DEFAULT, np.zeros(3), np.zeros(3)]
+    return [np.asarray(v, np.float64).reshape(1, -1) for v in vals]

@@ -108,6 +108,31 @@ def test_pdipm_matches_long_double_oracle(batch64, iters):
     assert worst[0] < tol_x and max(worst[1:]) < TOL_IP, worst
 
 
+def test_config1_single_t1_standing_batch_of_one():
+    """BASELINE configs[0]: one T1 biped, standing, horizon 10, 5 iterations -- and the reference's
+    real tick, 4 chained 5-iteration calls (mpc_controller_cusadi.py:144-169)."""
+    inp = bp.workload.config1_t1_standing()
+    qp_ref = co.qp_former(inp)
+    ins = _dev(inp)
+    _check_qp(_np(bp.qp_form(ins)), qp_ref)
+    ref5 = co.pdipm(qp_ref, 5, long_double=True)
+    ctx = bp.Context(1)
+    rot = torch.eye(3, dtype=torch.float32, device=DEV)[None]
+    w, x, s, z, y, res = ctx.solve(ins, rot, num_calls=1, iters_per_call=5, want_iterates=True)
+    for g, r in zip((x, s, z, y), ref5):
+        assert rel_err(g.cpu().numpy(), r) < TOL_IP
+    # 20 iterations: symmetric standing problem -> equal vertical forces approaching m g / 2 each
+    w20, x20 = ctx.solve(ins, rot, num_calls=4, iters_per_call=5, want_iterates=True)[:2]
+    ref20 = co.pdipm(qp_ref, 20, long_double=True)
+    assert rel_err(x20.cpu().numpy(), ref20[0]) < TOL_IP   # standing: no path sensitivity, 1e-9 holds at 20
+    u0 = x20[0, 120:132].cpu().numpy()
+    # left / right symmetric; the first-stage vertical force is the weight plus the tracking correction
+    assert abs(u0[2] - u0[5]) < 1e-4 * abs(u0[2])
+    assert abs(u0[2] + u0[5] - 40.0 * 9.81) < 0.15 * 40.0 * 9.81
+    assert tuple(w20.shape) == (1, 2, 6)
+    ctx.close()
+
+
 def test_pdipm_explicit_start_and_continuation(batch64):
     """10 inputs given explicitly (no cold-start flag) and 5+5 == 10 bit for bit."""
     inp, _ = batch64

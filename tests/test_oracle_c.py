@@ -56,3 +56,29 @@ def test_c_pdipm_matches_numpy_dense_oracle():
     d = co.pdipm(qp, 5)
     for i in range(6):
         assert np.array_equal(c[i], d[i])
+
+
+def test_config1_single_t1_standing_oracles_agree():
+    """BASELINE configs[0] (single T1 biped, standing, batch 1): numpy restatement == C restatement ==
+    80-bit build, and the emulated kernel code reproduces it; the standing solution carries the weight."""
+    from helpers import emul_pdipm
+    inp = bp.workload.config1_t1_standing()
+    qp_c, qp_np = co.qp_former(inp), oracle_qp_batch(inp)
+    for a, b in zip(qp_c, qp_np):
+        assert np.abs(a - b).max() <= 2e-15 * max(1.0, np.abs(b).max())
+    # one iteration: all four evaluations agree.  Later the standing problem drives s to the 1e-8 clamp
+    # and the numpy restatement's dense pivoted LU of the full KKT drifts (z: 7e-7 at 5 iterations,
+    # 4e-4 at 10) while the no-pivot LDL^T in 64 and 80 bits and the kernel's block elimination stay
+    # within 1e-10 of each other up to 20 iterations (DESIGN.md, "Accuracy")
+    l1, n1 = co.pdipm(qp_c, 1, long_double=True), oracle_ip_batch(qp_c, 1)
+    for i in range(4):
+        assert rel_err(n1[i], l1[i]) < 1e-9
+    for it in (5, 20):
+        d, l = co.pdipm(qp_c, it), co.pdipm(qp_c, it, long_double=True)
+        k, _ = emul_pdipm(qp_c, it)
+        for i in range(4):
+            assert rel_err(d[i], l[i]) < 1e-9 and rel_err(k[i], l[i]) < 1e-9
+    l20 = co.pdipm(qp_c, 20, long_double=True)
+    u0 = l20[0][0, 120:132]
+    # left / right symmetric; the first-stage vertical force is the weight plus the tracking correction
+    assert abs(u0[2] - u0[5]) < 1e-4 * abs(u0[2]) and abs(u0[2] + u0[5] - 40.0 * 9.81) < 0.15 * 40.0 * 9.81
