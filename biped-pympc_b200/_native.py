@@ -27,7 +27,7 @@ _PP = ctypes.POINTER(_P)
 EXPORTED_SYMBOLS = (
     "srbd_version", "srbd_error_string", "srbd_last_cuda_error", "srbd_init",
     "srbd_qp_former_nnz_in", "srbd_qp_former_nnz_out", "srbd_pdipm_nnz_in", "srbd_pdipm_nnz_out",
-    "srbd_pattern", "srbd_qp_form", "srbd_pdipm_work_doubles", "srbd_pdipm", "srbd_wrench",
+    "srbd_pattern", "srbd_qp_form", "srbd_pdipm_work_doubles", "srbd_pdipm", "srbd_pdipm_is_stage_invariant", "srbd_wrench",
     "srbd_ctx_create", "srbd_ctx_destroy", "srbd_mpc_solve", "srbd_mpc_solve_host",
     "srbd_qp_former_evaluate", "srbd_sparse_pdipm_multiple_iterations_evaluate", "srbd_dfma_peak",
 )
@@ -60,6 +60,7 @@ def load(build_if_missing: bool = True):
     lib.srbd_pdipm_work_doubles.restype = ctypes.c_size_t
     lib.srbd_pdipm_work_doubles.argtypes = [ci]
     lib.srbd_pdipm.argtypes = [vp, vp, vp, vp, ci, ci, cd, cu, vp]
+    lib.srbd_pdipm_is_stage_invariant.argtypes = [vp, ci, vp, ctypes.POINTER(ci)]
     lib.srbd_wrench.argtypes = [vp, vp, vp, ci, vp]
     lib.srbd_ctx_create.argtypes = [ctypes.POINTER(vp), ci, ci]
     lib.srbd_ctx_destroy.argtypes = [vp]
@@ -140,6 +141,18 @@ def qp_form(inputs: Sequence, out: Optional[List] = None) -> List:
     with torch.cuda.device(dev):
         check(lib.srbd_qp_form(_ptr_array(ins), _ptr_array(out), B, _stream()))
     return out
+
+
+def is_stage_invariant(inputs: Sequence) -> bool:
+    """Synchronous probe: True when [Q_val, G_val, A_val, ...] is qp_former-shaped for every env
+    (identical stage blocks, unit coefficients on x_{k+1} / Mx rows), i.e. the fast kernel applies."""
+    import torch
+    lib = load()
+    chk, B = _check_inputs(list(inputs[:3]), IP_NNZ_IN[:3])
+    res = ctypes.c_int(0)
+    with torch.cuda.device(chk[0].device):
+        check(lib.srbd_pdipm_is_stage_invariant(_ptr_array(chk + [None] * 7, allow_none=True), B, _stream(), ctypes.byref(res)))
+    return bool(res.value)
 
 
 def pdipm(inputs: Sequence, num_iters: int = 5, tol: float = 0.0, cold_start: bool = False,

@@ -186,6 +186,26 @@ int srbd_pdipm(const double* const* in10, double* const* out6, double* work, int
   return SRBD_OK;
 }
 
+int srbd_pdipm_is_stage_invariant(const double* const* in10, int B, void* stream, int* result) {
+  if (!in10 || !in10[IP_Q] || !in10[IP_G] || !in10[IP_A] || !result || B < 0) return SRBD_EINVAL;
+  *result = 1;
+  if (B == 0) return SRBD_OK;
+  int rc = ensure_init();
+  if (rc) return rc;
+  int* flag = nullptr;
+  SRBD_CUDA(cudaMalloc((void**)&flag, sizeof(int)));
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), st);
+  if (e == cudaSuccess) e = launch_stage_invariant_probe(in10[IP_Q], in10[IP_G], in10[IP_A], flag, B, st);
+  int h = 1;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(flag);
+  if (e != cudaSuccess) return cuda_fail(e);
+  *result = (h == 0);
+  return SRBD_OK;
+}
+
 int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, int B, void* stream) {
   if (!x_sol || !rotation_body || !wrench || B < 0) return SRBD_EINVAL;
   SRBD_CUDA(launch_wrench(x_sol, rotation_body, wrench, B, (cudaStream_t)stream));
@@ -402,8 +422,12 @@ float srbd_sparse_pdipm_multiple_iterations_evaluate(const double** inputs, doub
     g_compat_work_B = (size_t)batch_size;
   }
   return compat_eval<IP_N_IN, IP_N_OUT>(inputs, outputs, batch_size, [&](const double** hin, double** hout) {
-    // arbitrary values on the frozen pattern are accepted: no stage-invariance assumption
-    return srbd_pdipm(hin, hout, g_compat_work, nullptr, batch_size, 5, 0.0, 0u, nullptr);
+    // arbitrary values on the frozen pattern are accepted; the call is synchronous by contract, so
+    // the data is probed first and qp_former-shaped batches take the fast kernel
+    int inv = 0;
+    int rc = srbd_pdipm_is_stage_invariant(hin, batch_size, nullptr, &inv);
+    if (rc) return rc;
+    return srbd_pdipm(hin, hout, g_compat_work, nullptr, batch_size, 5, 0.0, inv ? SRBD_STAGE_INVARIANT : 0u, nullptr);
   });
 }
 

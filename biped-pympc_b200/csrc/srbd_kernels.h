@@ -18,6 +18,9 @@ int pdipm_warps_per_cta(bool stage_invariant);
 // u0 -> body-frame wrench (mpc_controller_cusadi.py:186-203)
 cudaError_t launch_wrench(const double* x_sol, const float* rotation_body_rowmajor, float* wrench,
                           int B, cudaStream_t stream);
+// *flag |= 1 unless every env carries stage-invariant, unit-E data (what qp_former produces)
+cudaError_t launch_stage_invariant_probe(const double* Q, const double* G, const double* A, int* flag, int B,
+                                         cudaStream_t stream);
 // DFMA micro-benchmark used for the FP64 roofline denominator
 cudaError_t launch_dfma_peak(double* sink, int iters, int blocks, int threads, cudaStream_t stream);
 

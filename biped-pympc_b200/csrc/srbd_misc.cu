@@ -42,6 +42,33 @@ cudaError_t launch_wrench(const double* x_sol, const float* rot, float* wrench, 
   return cudaGetLastError();
 }
 
+// Probe used by the synchronous drop-in entry: does every env of the batch carry qp_former-shaped
+// data (Q / G / A values identical for every horizon stage, unit coefficients on x_{k+1} and on
+// the Mx rows)?  One warp per env, 1 716 doubles read per env; *flag is OR-ed with 1 otherwise.
+__global__ void stage_invariant_probe_kernel(const double* __restrict__ Q, const double* __restrict__ G,
+                                             const double* __restrict__ A, int* flag, int B) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const double* q = Q + (long long)warp * NNZ_H;
+  const double* g = G + (long long)warp * NNZ_G;
+  const double* a = A + (long long)warp * NNZ_A;
+  int bad = 0;
+  for (int i = lane; i < 36 * 8; i += 32) bad |= (a[36 + i] != a[i % 36]);              // x-columns, stages 1..8
+  for (int c = lane; c < 12; c += 32) bad |= (a[324 + c] != 1.0) | (a[a_xcol_off(c)] != 1.0);   // E
+  for (int i = lane; i < 86 * 9; i += 32) bad |= (a[336 + 86 + i] != a[336 + i % 86]);  // u-columns
+  if (lane < 2) bad |= (a[336 + a_ucol_off(6 + 3 * lane) + A_UCOL_MX_POS] != 1.0);      // Mx rows
+  for (int i = lane; i < 28 * 9; i += 32) bad |= (g[28 + i] != g[i % 28]);
+  for (int i = lane; i < 108; i += 32) bad |= (q[12 + i] != q[i % 12]) | (q[132 + i] != q[120 + i % 12]);
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flag, 1);
+}
+
+cudaError_t launch_stage_invariant_probe(const double* Q, const double* G, const double* A, int* flag, int B,
+                                         cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  stage_invariant_probe_kernel<<<(B + 7) / 8, 256, 0, stream>>>(Q, G, A, flag, B);
+  return cudaGetLastError();
+}
+
 // 8 independent DFMA chains per thread; 16 flop per inner iteration per thread.
 __global__ void dfma_peak_kernel(double* sink, int iters) {
   double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

@@ -76,7 +76,7 @@ class B200Function:
     """``CusadiFunction``-compatible operator backed by the hand-written sm_100a kernels."""
 
     def __init__(self, fn, num_instances: int, device="cuda", num_iters: int = 5, tol: float = 0.0,
-                 stage_invariant: bool = False):
+                 stage_invariant=None):
         import torch
         if isinstance(fn, str):
             fn = {"qp_former": QP_FORMER_FUNCTION, "sparse_pdipm_multiple_iterations": PDIPM_FUNCTION}[fn]
@@ -88,7 +88,10 @@ class B200Function:
         self.fn_casadi = fn
         self.fn_name = fn.name()
         self.num_instances = int(num_instances)
-        self.num_iters, self.tol, self.stage_invariant = int(num_iters), float(tol), bool(stage_invariant)
+        # stage_invariant: True / False force the fast / general kernel; None (default) probes every
+        # batch (the reference's evaluate is synchronous too, CusadiFunction.py:43) and picks the fast
+        # kernel for qp_former-shaped data
+        self.num_iters, self.tol, self.stage_invariant = int(num_iters), float(tol), stage_invariant
         self._device = torch.device(device)
         self.eval_time = 0.0
         B = self.num_instances
@@ -111,7 +114,10 @@ class B200Function:
         if self.fn_name == "qp_former":
             _native.qp_form(inputs, out=self._output_tensors)
         else:
-            _native.pdipm(inputs, num_iters=self.num_iters, tol=self.tol, stage_invariant=self.stage_invariant,
+            inv = self.stage_invariant
+            if inv is None:
+                inv = _native.is_stage_invariant(inputs)
+            _native.pdipm(inputs, num_iters=self.num_iters, tol=self.tol, stage_invariant=bool(inv),
                           out=self._output_tensors, work=self._work, iters_done=self.iters_done)
 
     def getDenseOutput(self, out_idx: int):

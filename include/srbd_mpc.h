@@ -47,8 +47,10 @@ extern "C" {
 #define SRBD_COLD_START 1u        /* start from x=0, s=max(h,1), z=1, y=1
                                      (mpc_controller_cusadi.py:138-141); in[x,s,z,y] ignored  */
 #define SRBD_STAGE_INVARIANT 2u   /* caller guarantees Q/G/A values are identical for every
-                                     horizon stage (true for anything qp_former produced);
-                                     selects the shared-memory-resident fast path           */
+                                     horizon stage, with unit coefficients on x_{k+1} and on the
+                                     Mx rows (true for anything qp_former produced); selects the
+                                     fast kernel.  Non-unit coefficients are detected per env and
+                                     reported as NaN iterates / iters_done = -1               */
 
 #define SRBD_NZ 240
 #define SRBD_NEQ 140
@@ -95,6 +97,12 @@ size_t srbd_pdipm_work_doubles(int B);
 int srbd_pdipm(const double* const* in10, double* const* out6, double* work, int* iters_done,
                int B, int num_iters, double tol, unsigned flags, void* stream);
 
+/* SYNCHRONOUS probe: *result = 1 when every env of the batch carries stage-invariant data with
+ * unit coefficients on x_{k+1} and on the Mx rows (true for anything qp_former produced), i.e. when
+ * SRBD_STAGE_INVARIANT may be passed to srbd_pdipm.  Used by the CusADi-compatible entry, which is
+ * synchronous anyway (generateCUDACode.py:166-177), to pick the fast kernel by itself. */
+int srbd_pdipm_is_stage_invariant(const double* const* in10, int B, void* stream, int* result);
+
 /* u0 = x[120:132] -> body-frame wrench (B,2,6) fp32, mpc_controller_cusadi.py:186-203.
  * rotation_body: device fp32 (B,3,3) row-major. */
 int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, int B, void* stream);
@@ -110,8 +118,13 @@ int srbd_mpc_solve(srbd_ctx* ctx, const double* const* in17, const float* rotati
                    int num_calls, int iters_per_call, double tol,
                    float* wrench, double* x_out, double* s_out, double* z_out, double* y_out,
                    double* res_out, int* iters_done, void* stream);
-/* the same with HOST buffers (pinned or pageable): copies the 17 inputs + rotation in, runs,
- * copies the wrench (and, when not NULL, x_out and res_out) back, and synchronises. */
+/* the same with HOST buffers, synchronous.  Page-locked (pinned) buffers are read and written in
+ * place over PCIe by the kernels (UVA mapping); pageable ones are staged with cudaMemcpyAsync.  The
+ * batch is cut into chunks that alternate between two internal streams so that the input traffic
+ * of one chunk overlaps the solve of the previous one.  in17_host[1] / [2] (x, u: the linearisation
+ * point, dead for this LTV-linear problem) may be NULL = all ones, the constant the reference call
+ * site passes (mpc_controller_cusadi.py:55-56); the same holds for in17[1] / [2] of srbd_qp_form
+ * and srbd_mpc_solve. */
 int srbd_mpc_solve_host(srbd_ctx* ctx, const double* const* in17_host, const float* rotation_body_host,
                         int B, int num_calls, int iters_per_call, double tol,
                         float* wrench_host, double* x_out_host, double* res_out_host);
@@ -121,7 +134,9 @@ int srbd_mpc_solve_host(srbd_ctx* ctx, const double* const* in17_host, const flo
  * are DEVICE arrays of device pointers, `work` is ignored (the kernels keep their        *
  * scratch in shared memory / an internal buffer), the call runs on the legacy default    *
  * stream, is synchronous and returns the kernel time in seconds (negative on error).     *
- * The PDIPM variant performs the reference's fixed 5 Newton iterations.                  */
+ * The PDIPM variant performs the reference's fixed 5 Newton iterations; it probes the    *
+ * batch (srbd_pdipm_is_stage_invariant) and takes the fast kernel for qp_former-shaped   *
+ * data, the general kernel for arbitrary values on the frozen pattern.                   */
 float srbd_qp_former_evaluate(const double** inputs, double* work, double** outputs, int batch_size);
 float srbd_sparse_pdipm_multiple_iterations_evaluate(const double** inputs, double* work, double** outputs,
                                                       int batch_size);

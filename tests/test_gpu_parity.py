@@ -323,6 +323,24 @@ def test_host_entry_chunks_and_default_linearisation_point(pinned):
     ctx.close()
 
 
+def test_stage_invariance_probe_and_auto_dispatch(golden):
+    """The synchronous drop-in entries probe the batch and take the fast kernel for qp_former data."""
+    qp = [golden[f"qp_{n}"] for n in "HfAbGd"]
+    Hv, f, Av, b, Gv, d = _dev(qp)
+    assert bp.is_stage_invariant([Hv, Gv, Av]) is True
+    for arr, idx in ((Av, 36 + 40), (Gv, 28 * 3 + 5), (Hv, 12 * 7 + 2), (Av, 336 + 86 * 4 + 17)):
+        t = arr.clone(); t[1, idx] += 1e-9
+        trial = [t if a is arr else a for a in (Hv, Gv, Av)]
+        assert bp.is_stage_invariant(trial) is False
+    B = Hv.shape[0]
+    fn = bp.B200Function("sparse_pdipm_multiple_iterations", B)          # default: probe
+    x = torch.zeros(B, 240, dtype=torch.float64, device=DEV)
+    s = torch.maximum(d, torch.ones_like(d)); z = torch.ones_like(d); y = torch.ones(B, 140, dtype=torch.float64, device=DEV)
+    fn.evaluate([Hv, Gv, Av, f, d, b, x, s, z, y])
+    fast = bp.pdipm([Hv, Gv, Av, f, d, b, x, s, z, y], num_iters=5, stage_invariant=True)
+    assert torch.equal(fn.outputs_sparse[0], fast[0])
+
+
 def test_fast_path_rejects_data_that_is_not_qp_former_shaped(golden):
     """SRBD_STAGE_INVARIANT promises unit coefficients on x_{k+1} / Mx rows; anything else must
     fail loudly (NaN iterates, iteration count -1), never silently solve another problem."""
