@@ -63,17 +63,23 @@ inline WarpEmulState*& emul_state() {
   static thread_local WarpEmulState* s = nullptr;
   return s;
 }
+inline int& emul_order() {
+  static int order = 1;
+  return order;
+}
 
 struct Warp {
   int lane_;
   int lane() const { return lane_; }
-  // yield to the next unfinished lane (round robin)
+  // yield to the next unfinished lane (round robin; emul_order() = -1 walks the lanes in the
+  // opposite direction: a kernel without intra-interval races gives bit-identical results)
   static void yield() {
     WarpEmulState* st = emul_state();
     int me = st->cur;
     int nxt = me;
+    const int dir = emul_order() < 0 ? WarpEmulState::kLanes - 1 : 1;
     for (int i = 1; i <= WarpEmulState::kLanes; ++i) {
-      int c = (me + i) % WarpEmulState::kLanes;
+      int c = (me + i * dir) % WarpEmulState::kLanes;
       if (!st->done[c]) { nxt = c; break; }
     }
     if (nxt == me) return;
@@ -119,8 +125,9 @@ inline void emul_lane_entry(int lane) {
   st->body(lane);
   st->done[lane] = true;
   // hand over to another unfinished lane, or back to main
+  const int dir = emul_order() < 0 ? WarpEmulState::kLanes - 1 : 1;
   for (int i = 1; i <= WarpEmulState::kLanes; ++i) {
-    int c = (lane + i) % WarpEmulState::kLanes;
+    int c = (lane + i * dir) % WarpEmulState::kLanes;
     if (!st->done[c]) {
       st->cur = c;
       setcontext(&st->lane_ctx[c]);
@@ -143,8 +150,8 @@ inline void run_warp(const std::function<void(int)>& body, size_t stack_bytes = 
     st.lane_ctx[l].uc_link = &st.main_ctx;
     makecontext(&st.lane_ctx[l], (void (*)())emul_lane_entry, 1, l);
   }
-  st.cur = 0;
-  swapcontext(&st.main_ctx, &st.lane_ctx[0]);
+  st.cur = emul_order() < 0 ? WarpEmulState::kLanes - 1 : 0;
+  swapcontext(&st.main_ctx, &st.lane_ctx[st.cur]);
   emul_state() = nullptr;
 }
 

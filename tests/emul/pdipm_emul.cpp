@@ -68,6 +68,9 @@ extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, d
   return 0;
 }
 
+// lane scheduling order of the emulated warp between barriers: +1 ascending, -1 descending
+extern "C" void srbd_emul_set_order(int order) { emul_order() = order < 0 ? -1 : 1; }
+
 extern "C" int srbd_emul_trace_get(const char* tag, double* out, int n) {
   auto it = g_trace.find(tag);
   if (it == g_trace.end()) return -1;

@@ -27,6 +27,17 @@ def test_emulated_kernel_matches_oracle_5_iters(qp_small, uniform):
     assert rel_err(got[4], ref[4]) < 1e-8 and rel_err(got[5], ref[5]) < 1e-8
 
 
+@pytest.mark.parametrize("uniform", [True, False])
+def test_no_race_between_warp_barriers(qp_small, uniform):
+    """The emulator runs the 32 lanes one after the other between two warp barriers.  A lane that
+    reads what another lane writes inside the same interval (a missing __syncwarp) gets a different
+    value when the lanes are walked in the opposite direction: results must be bit-identical."""
+    a, _ = emul_pdipm(qp_small, 3, uniform=uniform, lane_order=1)
+    b, _ = emul_pdipm(qp_small, 3, uniform=uniform, lane_order=-1)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
+
+
 def test_emulated_kernel_against_golden(golden):
     qp = [golden[f"qp_{n}"] for n in ("H", "f", "A", "b", "G", "d")]
     got, _ = emul_pdipm(qp, 5)
