@@ -226,14 +226,14 @@ def run_b200(args):
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": (f"{B}-env batched SRBD MPC per GPU, 5 PDIPM iters, fp64, cold start "
-                                "(BASELINE configs[1]); form + solve + wrench via srbd_mpc_solve") if default_wl else
+                                "(BASELINE configs[1]); form + solve + wrench fused in one kernel via srbd_mpc_solve") if default_wl else
                                (f"{B}-env batched SRBD MPC per GPU, {args.calls} x {args.iters} PDIPM iters"
                                 + (f" or tol {args.tol:g}" if args.tol > 0 else "") + ", fp64, cold start; srbd_mpc_solve"),
                    "envs_per_gpu": B, "iters": args.calls * args.iters, "horizon": 10, "parallelism": f"env-sharded x{world}, no collective",
                    "l2": "256 MB buffer written between timed iterations (L2 flush)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": n_e2e, "api": "srbd_mpc_solve_host (pinned host buffers read and written in place over PCIe by the kernels; two 2058-env chunks on two streams)"},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": args.steps,          # ONE kernel per step: fused assembly + PDIPM + wrench (pdipm_fast_kernel)
         "clocks": clocks,
     }
     ts = sorted(times_ms)

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -106,6 +107,7 @@ struct srbd_ctx {
   cudaStream_t stream = nullptr;          // used by the host entry (chunks alternate between
   cudaStream_t stream2 = nullptr;         // the two streams so that copies overlap the solve)
   cudaEvent_t done2 = nullptr;
+  bool unfused = false;                   // SRBD_TICK_UNFUSED=1: assembly, solve and wrench as three launches
 };
 
 extern "C" {
@@ -182,6 +184,8 @@ int srbd_pdipm(const double* const* in10, double* const* out6, double* work, int
   }
   for (int i = 0; i < IP_N_OUT; ++i) { if (!out6[i]) return SRBD_EINVAL; a.out[i] = out6[i]; }
   a.work = work; a.iters_done = iters_done; a.num_iters = num_iters; a.tol = tol; a.cold_start = cold ? 1 : 0;
+  a.fused = 0; a.rot = nullptr; a.wrench = nullptr;
+  for (int i = 0; i < QP_N_IN; ++i) a.qp_in[i] = nullptr;
   SRBD_CUDA(launch_pdipm(a, B, (flags & SRBD_STAGE_INVARIANT) != 0, num_sms(), (cudaStream_t)stream));
   return SRBD_OK;
 }
@@ -237,6 +241,7 @@ int srbd_ctx_create(srbd_ctx** out, int max_B, int device) {
   if (!c) return SRBD_ENOMEM;
   cudaGetDevice(&c->device);
   c->max_B = max_B;
+  { const char* ev = std::getenv("SRBD_TICK_UNFUSED"); c->unfused = ev && ev[0] == '1'; }
   const size_t B = (size_t)max_B;
   bool ok = true;
   auto alloc = [&](void** p, size_t bytes) { if (ok && cudaMalloc(p, bytes) != cudaSuccess) ok = false; };
@@ -266,15 +271,32 @@ int solve_range(srbd_ctx* c, const double* const* in17, const float* rotation_bo
                 int iters, double tol, float* wrench, double* x_out, double* s_out, double* z_out,
                 double* y_out, double* res_out, int* iters_done, cudaStream_t st) {
   const size_t o = (size_t)env0;
-  double* qp[QP_N_OUT];
-  for (int i = 0; i < QP_N_OUT; ++i) qp[i] = c->qp_out[i] + o * kQpNnzOut[i];
-  int rc = srbd_qp_form(in17, qp, B, st);
-  if (rc) return rc;
   double* x = x_out ? x_out : c->it[0] + o * NZ;
   double* s = s_out ? s_out : c->it[1] + o * NINEQ;
   double* z = z_out ? z_out : c->it[2] + o * NINEQ;
   double* y = y_out ? y_out : c->it[3] + o * NEQ;
   double* res = res_out ? res_out : c->res + o * 4;
+  if (!c->unfused) {
+    // ONE launch: the PDIPM kernel assembles its stage data from the 17 inputs (no CCS round trip
+    // through HBM), iterates, and writes the wrench
+    int rc = ensure_init();
+    if (rc) return rc;
+    PdipmArgs a;
+    for (int i = 0; i < IP_N_IN; ++i) a.in[i] = nullptr;
+    for (int i = 0; i < QP_N_IN; ++i) {
+      if (!in17[i] && i != IN_X && i != IN_U) return SRBD_EINVAL;
+      a.qp_in[i] = in17[i];
+    }
+    a.out[IPO_X] = x; a.out[IPO_S] = s; a.out[IPO_Z] = z; a.out[IPO_Y] = y; a.out[IPO_RES] = res; a.out[IPO_MU] = c->mu + o;
+    a.work = c->work + o * PDIPM_WORK_DOUBLES; a.iters_done = iters_done; a.num_iters = iters; a.tol = tol;
+    a.cold_start = 1; a.fused = 1; a.rot = rotation_body; a.wrench = wrench;
+    SRBD_CUDA(launch_pdipm(a, B, true, num_sms(), st));
+    return SRBD_OK;
+  }
+  double* qp[QP_N_OUT];
+  for (int i = 0; i < QP_N_OUT; ++i) qp[i] = c->qp_out[i] + o * kQpNnzOut[i];
+  int rc = srbd_qp_form(in17, qp, B, st);
+  if (rc) return rc;
   const double* in10[IP_N_IN] = {qp[OUT_H], qp[OUT_G], qp[OUT_A], qp[OUT_F], qp[OUT_D], qp[OUT_B],
                                  nullptr, nullptr, nullptr, nullptr};
   double* out6[IP_N_OUT] = {x, s, z, y, res, c->mu + o};

@@ -20,6 +20,12 @@ struct PdipmArgs {
   double tol;                   // <= 0: fixed iteration count; > 0: stop when rx,rs,re,mu < tol
   int cold_start;               // 1: ignore in[x,s,z,y]; start from x=0, s=max(h,1), z=1, y=1
                                 //    (mpc_controller_cusadi.py:138-141)
+  // ---- fused tick (fast kernel only): assemble from the 17 qp_former inputs instead of reading
+  //      the CCS vectors in[0..5], and turn u0 into the body-frame wrench at the end
+  int fused;                    // 1: qp_in[] is used, in[0..5] are ignored
+  const double* qp_in[QP_N_IN]; // qp_former inputs (x, u may be null = ones)
+  const float* rot;             // optional (B,3,3) fp32 row-major state-estimate rotation
+  float* wrench;                // optional (B,2,6) fp32 (mpc_controller_cusadi.py:186-203)
 };
 constexpr int PDIPM_WORK_DOUBLES = 1344;  // dx,dy,ds,dz (affine) + D, 1/W, D*g, r2 per inequality row
 

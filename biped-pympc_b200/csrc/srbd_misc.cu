@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "srbd_kernels.h"
+#include "srbd_pdipm_fast.h"
 
 namespace srbd {
 
@@ -18,22 +19,9 @@ __global__ void wrench_kernel(const double* __restrict__ x_sol, const float* __r
   float R[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) R[i] = rot[(long long)e * 9 + i];
-  float v[4][3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    v[0][i] = (float)u0[i];        // f_L
-    v[1][i] = (float)u0[6 + i];    // m_L
-    v[2][i] = (float)u0[3 + i];    // f_R
-    v[3][i] = (float)u0[9 + i];    // m_R
-  }
-  v[1][0] = 0.f;
-  v[3][0] = 0.f;
   float* o = wrench + (long long)e * 12;
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-#pragma unroll
-    for (int i = 0; i < 3; ++i)   // (R' v)_i = sum_j R[j][i] v_j
-      o[3 * q + i] = -(R[0 + i] * v[q][0] + R[3 + i] * v[q][1] + R[6 + i] * v[q][2]);
+  for (int idx = 0; idx < 12; ++idx) o[idx] = wrench_entry(u0, R, idx);   // shared with the fused tick
 }
 
 cudaError_t launch_wrench(const double* x_sol, const float* rot, float* wrench, int B, cudaStream_t stream) {

@@ -23,6 +23,7 @@
 #pragma once
 
 #include "srbd_pdipm_core.h"
+#include "srbd_qp_table.h"
 
 namespace srbd {
 
@@ -55,7 +56,9 @@ struct FastSmem {
   static constexpr int SIZE = OFF_FB + FB_SIZE;   // 2066
 };
 // lane-private per-row scratch in the work buffer
-enum : int { FW_DX = 0, FW_DY = 240, FW_S = 380, FW_Z = 540, FW_Q = 700, FW_END = 860 };
+enum : int { FW_DX = 0, FW_DY = 240, FW_S = 380, FW_Z = 540, FW_Q = 700,
+             // fused tick only: f of the states, c_d | c_d + A_d x0, F_max * contact
+             FW_FX = 860, FW_CD = 980, FW_FC = 1004, FW_END = 1024 };
 static_assert(FW_END <= PDIPM_WORK_DOUBLES, "work buffer too small");
 
 // host: gather table of the fast path from the table of srbd_stage_table.h
@@ -68,6 +71,17 @@ inline void build_fast_slots(const StageSlot* sb, StageSlot* fs) {
   for (int i = 0; i < 12; ++i) fs[FB_HU + i] = sb[SB_HU + i];
   for (int i = 0; i < 12; ++i) fs[FB_RAW + i] = sb[SB_E + i];
   for (int i = 0; i < 2; ++i) fs[FB_RAW + 12 + i] = sb[SB_MX + i];
+}
+
+// entry q*3+i of the (2,6) body-frame wrench of one env: rows [-R' f_L, -R' m_L ; -R' f_R, -R' m_R]
+// with m_x zeroed and the cast to fp32 done before the rotation, exactly as
+// mpc_controller_cusadi.py:186-203.  R: row-major fp32 state-estimate rotation.
+SRBD_DEV float wrench_entry(const double* u0, const float* R, int idx) {
+  const int q = idx / 3, i = idx - 3 * q;
+  const int base = (q == 0) ? 0 : (q == 1 ? 6 : (q == 2 ? 3 : 9));   // f_L, m_L, f_R, m_R
+  float v0 = (float)u0[base], v1 = (float)u0[base + 1], v2 = (float)u0[base + 2];
+  if (q == 1 || q == 3) v0 = 0.f;
+  return -(R[0 + i] * v0 + R[3 + i] * v1 + R[6 + i] * v2);
 }
 
 struct PdipmFast {
@@ -113,6 +127,8 @@ struct PdipmFast {
   SRBD_DEV int setup() {
     double* f = fb();
     int bad = 0;
+    if (pa->fused) gather_fused();
+    else {
     const double* gQ = gin(IP_Q, NNZ_H); const double* gG = gin(IP_G, NNZ_G); const double* gA = gin(IP_A, NNZ_A);
     for (int i = lane; i < FB_NSLOT; i += 32) {
       const StageSlot sl = slots[i];
@@ -130,6 +146,7 @@ struct PdipmFast {
     }
     for (int m = 16; m >= 1; m >>= 1) bad |= w.shfl_i(bad, lane ^ m);
     w.sync();
+    }
     const int q = rr;
     f[FB_PHX + q] = rcp(f[FB_HX + q] + IP_BETA);
     if (r < 2) {
@@ -212,6 +229,47 @@ struct PdipmFast {
     }
     w.sync();
     return bad;
+  }
+
+  // fused tick: the gathered part of the stage data straight from the 17 qp_former inputs (the
+  // value table of srbd_qp_table.h is built in the scratch that later holds P), plus the three
+  // stage-dependent vectors the residual phase needs, parked in the work buffer
+  SRBD_DEV void gather_fused() {
+    double* f = fb();
+    double* V = sm + SM::OFF_P;           // V_COUNT
+    double* Wr = V + 232;                 // RW_COUNT
+    qp_value_table(pa->qp_in, e, lane, w, V, Wr);
+    for (int i = lane; i < 168; i += 32) { const int rw = i / 14, c = i - 14 * rw; f[FB_B + i] = c < 12 ? V[V_NBD + 12 * rw + c] : 0.0; }
+    if (lane < 12) { f[FB_AB + lane] = V[V_NEG1]; f[FB_HX + lane] = V[V_Q + lane]; f[FB_HU + lane] = V[V_R + lane]; }
+    if (lane < 9) f[FB_AB + 12 + lane] = V[V_NADTR + lane];
+    if (lane < 3) f[FB_AB + 21 + lane] = V[V_NADT];
+    if (lane < 28) {   // G values of a stage: two feet x 12, then the two my columns (srbd_pattern.h)
+      const int q = lane < 24 ? lane % 12 : lane - 24;
+      int v;
+      if (lane < 24) v = (q == 0 || q == 2 || q == 10) ? V_NEG1 : (q == 1 || q == 3 || q == 11) ? V_ONE : q < 8 ? V_NEGMU : (q == 8 ? V_NEGLT : V_NEGLH);
+      else v = (q & 1) ? V_ONE : V_NEG1;
+      f[FB_G + lane] = V[v];
+    }
+    double* ws = gws();
+    {   // f_x = grad - H z evaluated as the assembly kernel does (srbd_constraints.py:67-69)
+      const double* xr = pa->qp_in[IN_XREF] + e * 120;
+      const double* xl = pa->qp_in[IN_X] ? pa->qp_in[IN_X] + e * 120 : nullptr;
+      int m12 = lane % 12;
+      for (int i = lane; i < 120; i += 32) {
+        const double xv = xl ? xl[i] : 1.0, q = V[V_Q + m12];
+        ws[FW_FX + i] = q * (xv - xr[i]) - q * xv;
+        m12 += 8; if (m12 >= 12) m12 -= 12;
+      }
+    }
+    if (lane < 24) ws[FW_CD + lane] = V[V_CD + lane];      // c_d (12) | c_d + A_d x0 (12)
+    if (lane < 20) ws[FW_FC + lane] = V[V_FC + lane];
+    w.sync();
+  }
+  // f, h, b of inequality row j / column rr of stage k, whichever mode
+  SRBD_DEV double h_of(int k, int j) const {
+    if (!pa->fused) return ldg(gin(IP_H, NINEQ) + j);
+    const int q = j & 7;
+    return q == 7 ? gws()[FW_FC + 2 * k + ((j >> 3) & 1)] : 0.0;
   }
 
   // ------------------------------------------------------------------------------------
@@ -528,9 +586,8 @@ struct PdipmFast {
     {
       double* oX = gout(IPO_X, NZ); double* oS = gout(IPO_S, NINEQ); double* oZ = gout(IPO_Z, NINEQ); double* oY = gout(IPO_Y, NEQ);
       if (A.cold_start) {
-        const double* gH = gin(IP_H, NINEQ);
         for (int i = lane; i < NZ; i += 32) oX[i] = 0.0;
-        for (int i = lane; i < NINEQ; i += 32) { oS[i] = fmax(ldg(gH + i), 1.0); oZ[i] = 1.0; }
+        for (int i = lane; i < NINEQ; i += 32) oZ[i] = 1.0;
         for (int i = lane; i < NEQ; i += 32) oY[i] = 1.0;
       } else {
         const double* ix = gin(IP_X, NZ); const double* is = gin(IP_S, NINEQ);
@@ -551,6 +608,11 @@ struct PdipmFast {
         }
         return -1;
       }
+      if (A.cold_start) {   // s = max(h, 1); in fused mode h only exists after the set-up
+#pragma unroll
+        for (int t = 0; t < 5; ++t) { const int k = h ? 9 - t : t, j = 16 * k + r; oS[j] = fmax(h_of(k, j), 1.0); }
+      }
+      w.sync();
     }
 
     double* vx = sm + SM::OFF_VX;
@@ -644,6 +706,8 @@ struct PdipmFast {
       gout(IPO_MU, 1)[0] = mu_new;
       if (A.iters_done) A.iters_done[e] = it;
     }
+    if (A.fused && A.wrench && lane < 12)   // u0 -> body-frame wrench (the x updates above are visible: w.sync())
+      A.wrench[e * 12 + lane] = wrench_entry(gout(IPO_X, NZ) + NX * N, A.rot + e * 9, lane);
     return it;
   }
 
@@ -657,7 +721,8 @@ struct PdipmFast {
     double* sy = sx + 240; double* xs = sx + 380;
     double* ws = gws();
     const double* oS = gout(IPO_S, NINEQ); const double* oZ = gout(IPO_Z, NINEQ);
-    const double* gF = gin(IP_F, NZ); const double* gH = gin(IP_H, NINEQ); const double* gB = gin(IP_B, NEQ);
+    const bool fused = pa->fused != 0;
+    const double* gF = gin(IP_F, NZ); const double* gB = gin(IP_B, NEQ);
     {
       const double* oX = gout(IPO_X, NZ); const double* oY = gout(IPO_Y, NEQ);
       int m12 = lane % 12;
@@ -677,9 +742,13 @@ struct PdipmFast {
     for (int t = 0; t < 5; ++t) {
       const int k = h ? 9 - t : t;
       const int j = 16 * k + r;
-      const double sv = oS[j], zv = oZ[j], hv = ldg(gH + j);
-      const double fu = ldg(gF + 120 + 12 * k + rr), fxv = ldg(gF + 12 * k + rr), bd = ldg(gB + 12 * k + rr);
-      const double bm = ldg(gB + 120 + 2 * k + (r & 1));
+      const double sv = oS[j], zv = oZ[j], hv = h_of(k, j);
+      double fu = 0.0, fxv, bd, bm = 0.0;           // fused: f_u = 0, b_mx = 0 by construction
+      if (fused) { fxv = ws[FW_FX + 12 * k + rr]; bd = ws[FW_CD + (k == 0 ? 12 : 0) + rr]; }
+      else {
+        fu = ldg(gF + 120 + 12 * k + rr); fxv = ldg(gF + 12 * k + rr); bd = ldg(gB + 12 * k + rr);
+        bm = ldg(gB + 120 + 2 * k + (r & 1));
+      }
       const double* u = sx + 120 + 12 * k;
       double* ps = psi(k);
       double* trd = tr();

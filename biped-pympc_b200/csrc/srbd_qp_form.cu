@@ -17,22 +17,9 @@
 
 #include "srbd_kernels.h"
 #include "srbd_pattern.h"
+#include "srbd_qp_table.h"
 
 namespace srbd {
-
-// ---- value-table layout -----------------------------------------------------------------
-enum : int {
-  V_ZERO = 0, V_ONE = 1, V_NEG1 = 2, V_NEGMU = 3, V_NEGLT = 4, V_NEGLH = 5,
-  V_Q = 6, V_R = 18,
-  V_NADTR = 30,   // -dt * R[i][j]  at 30 + 3i + j
-  V_NADT = 39,    // -dt
-  V_NBD = 40,     // -B_d[r][c]     at 40 + 12r + c
-  V_CD = 184,     // c_d
-  V_B0 = 196,     // c_d + A_d x0
-  V_FC = 208,     // F_max * contact[stage][foot] at 208 + 2*stage + foot
-  V_COUNT = 228
-};
-static_assert(V_COUNT <= 256, "tables are uint8");
 
 constexpr int TAB_H = 0, TAB_A = TAB_H + NNZ_H, TAB_B = TAB_A + NNZ_A, TAB_G = TAB_B + NEQ,
               TAB_D = TAB_G + NNZ_G, TAB_SIZE = TAB_D + NINEQ;   // 2016
@@ -93,11 +80,6 @@ cudaError_t qp_form_upload_table() {
   return cudaMemcpyToSymbol(g_qp_tab, h, TAB_SIZE);
 }
 
-// raw per-env inputs staged in shared memory
-enum : int { RW_RB = 0, RW_IW = 9, RW_BODY = 18, RW_LF = 21, RW_RF = 24, RW_RL = 27, RW_RA = 30,
-             RW_X0 = 33, RW_CT = 45, RW_DT = 65, RW_M = 66, RW_MU = 67, RW_IINV = 68, RW_BCW = 77,
-             RW_COUNT = 113 };   // BCW: 3 x 12 angular-acceleration map  I^-1 [skew(rL) skew(rR) I I]
-
 template <int kEnvs>
 __global__ void __launch_bounds__(32 * kEnvs)
 qp_form_kernel(QpFormArgs a, int B) {
@@ -118,109 +100,7 @@ qp_form_kernel(QpFormArgs a, int B) {
       const long long e = env0 + warp;
       double* V = sV[warp];
       double* W = sRaw[warp];
-      // ---- stage raw inputs (nnz order = CasADi column-major) ---------------------------
-      if (lane < 9) { W[RW_RB + lane] = a.in[IN_RBODY][e * 9 + lane]; W[RW_IW + lane] = a.in[IN_IWORLD][e * 9 + lane]; }
-      if (lane < 3) {
-        W[RW_BODY + lane] = a.in[IN_BODY][e * 3 + lane];
-        W[RW_LF + lane] = a.in[IN_LFOOT][e * 3 + lane];
-        W[RW_RF + lane] = a.in[IN_RFOOT][e * 3 + lane];
-        W[RW_RL + lane] = a.in[IN_RESLIN][e * 3 + lane];
-        W[RW_RA + lane] = a.in[IN_RESANG][e * 3 + lane];
-      }
-      if (lane < 12) {
-        W[RW_X0 + lane] = a.in[IN_X0][e * 12 + lane];
-        V[V_Q + lane] = a.in[IN_Q][e * 12 + lane];
-        V[V_R + lane] = a.in[IN_R][e * 12 + lane];
-      }
-      if (lane < 20) W[RW_CT + lane] = a.in[IN_CONTACT][e * 20 + lane];
-      if (lane == 0) {
-        W[RW_DT] = a.in[IN_DT][e]; W[RW_M] = a.in[IN_M][e]; W[RW_MU] = a.in[IN_MU][e];
-      }
-      __syncwarp();
-      const double dt = W[RW_DT], m = W[RW_M], mu = W[RW_MU];
-      const double hdt2 = dt * dt / 2;
-      // ---- I_world^-1 (adjugate / det); M(i,j) = Iw_flat[i + 3j] ------------------------
-      if (lane < 9) {
-        const double* M = W + RW_IW;
-        auto Mx = [&](int i, int j) { return M[i + 3 * j]; };
-        const double det = Mx(0, 0) * (Mx(1, 1) * Mx(2, 2) - Mx(1, 2) * Mx(2, 1))
-                         + Mx(0, 1) * (Mx(1, 2) * Mx(2, 0) - Mx(1, 0) * Mx(2, 2))
-                         + Mx(0, 2) * (Mx(1, 0) * Mx(2, 1) - Mx(1, 1) * Mx(2, 0));
-        const int i = lane / 3, j = lane % 3;
-        const int j1 = (j + 1) % 3, j2 = (j + 2) % 3, i1 = (i + 1) % 3, i2 = (i + 2) % 3;
-        W[RW_IINV + 3 * i + j] = (Mx(j1, i1) * Mx(j2, i2) - Mx(j1, i2) * Mx(j2, i1)) / det;
-      }
-      __syncwarp();
-      // ---- angular-acceleration map: I^-1 [skew(rL) | skew(rR) | I | I]   (3 x 12) ------
-      if (lane < 18) {
-        const int i = lane / 6, c = lane % 6, ft = c / 3, j = c % 3;
-        const double* foot = W + (ft == 0 ? RW_LF : RW_RF);
-        const double rx = foot[0] - W[RW_BODY + 0], ry = foot[1] - W[RW_BODY + 1], rz = foot[2] - W[RW_BODY + 2];
-        const double* Ii = W + RW_IINV + 3 * i;
-        double v;
-        if (j == 0) v = Ii[1] * rz - Ii[2] * ry;
-        else if (j == 1) v = Ii[2] * rx - Ii[0] * rz;
-        else v = Ii[0] * ry - Ii[1] * rx;
-        W[RW_BCW + 12 * i + c] = v;
-      } else if (lane < 27) {
-        const int i = (lane - 18) / 3, j = (lane - 18) % 3;
-        const double v = W[RW_IINV + 3 * i + j];
-        W[RW_BCW + 12 * i + 6 + j] = v;
-        W[RW_BCW + 12 * i + 9 + j] = v;
-      }
-      __syncwarp();
-      // ---- constants, -dt R, contact ----------------------------------------------------
-      if (lane == 0) {
-        V[V_ZERO] = 0.0; V[V_ONE] = 1.0; V[V_NEG1] = -1.0; V[V_NEGMU] = -mu;
-        V[V_NEGLT] = -LT; V[V_NEGLH] = -LH; V[V_NADT] = -dt;
-      }
-      if (lane < 9) {   // R(i,j) = Rb_flat[i + 3j]
-        const int i = lane / 3, j = lane % 3;
-        V[V_NADTR + 3 * i + j] = -(dt * W[RW_RB + i + 3 * j]);
-      }
-      if (lane < 20) {  // contact(stage, foot) = flat[stage + 10*foot]; F_max * contact
-        const int st = lane % 10, ft = lane / 10;
-        V[V_FC + 2 * st + ft] = F_MAX * W[RW_CT + lane];
-      }
-      // ---- -B_d (12 x 12) ----------------------------------------------------------------
-      for (int idx = lane; idx < 144; idx += 32) {
-        const int r = idx / 12, c = idx % 12;
-        double v = 0.0;
-        if (r < 3) {          // euler rows: dt^2/2 * R * Bc_omega
-          const double* Rb = W + RW_RB;
-          v = hdt2 * (Rb[r] * W[RW_BCW + c] + Rb[r + 3] * W[RW_BCW + 12 + c] + Rb[r + 6] * W[RW_BCW + 24 + c]);
-        } else if (r < 6) {   // position rows: dt^2/2 / m on f_L[r-3], f_R[r-3]
-          if (c < 6 && c % 3 == r - 3) v = hdt2 * (1.0 / m);
-        } else if (r < 9) {   // omega rows
-          v = dt * W[RW_BCW + 12 * (r - 6) + c];
-        } else {              // velocity rows
-          if (c < 6 && c % 3 == r - 9) v = dt * (1.0 / m);
-        }
-        V[V_NBD + idx] = -v;
-      }
-      // ---- c_d and b_0 = c_d + A_d x0 -----------------------------------------------------
-      if (lane < 12) {
-        const int r = lane, i = r % 3;
-        const double* Rb = W + RW_RB;
-        const double* x0 = W + RW_X0;
-        const double gl = (i == 2 ? GRAV_Z : 0.0) + W[RW_RL + i];   // gravity + residual lin accel
-        double cd, ax;
-        if (r < 3) {
-          cd = hdt2 * (Rb[i] * W[RW_RA] + Rb[i + 3] * W[RW_RA + 1] + Rb[i + 6] * W[RW_RA + 2]);
-          ax = x0[r] + dt * (Rb[i] * x0[6] + Rb[i + 3] * x0[7] + Rb[i + 6] * x0[8]);
-        } else if (r < 6) {
-          cd = hdt2 * gl;
-          ax = x0[r] + dt * x0[r + 6];
-        } else if (r < 9) {
-          cd = dt * W[RW_RA + i];
-          ax = x0[r];
-        } else {
-          cd = dt * gl;
-          ax = x0[r];
-        }
-        V[V_CD + r] = cd;
-        V[V_B0 + r] = cd + ax;
-      }
+      qp_value_table(a.in, e, lane, Warp(), V, W);
     }
     __syncthreads();
 

@@ -58,6 +58,8 @@ extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, d
   for (int i = 0; i < IP_N_IN; ++i) A.in[i] = in10[i];
   for (int i = 0; i < IP_N_OUT; ++i) A.out[i] = out6[i];
   A.work = work; A.iters_done = iters_done; A.num_iters = num_iters; A.tol = tol; A.cold_start = cold_start;
+  A.fused = 0; A.rot = nullptr; A.wrench = nullptr;
+  for (int i = 0; i < QP_N_IN; ++i) A.qp_in[i] = nullptr;
   g_trace_on = trace != 0;
   g_trace.clear();
   for (long long e = 0; e < B; ++e) {
@@ -65,6 +67,24 @@ extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, d
     else if (uniform) run_env<true>(A, e, slots, nullptr);
     else run_env<false>(A, e, slots, nullptr);
   }
+  return 0;
+}
+
+// fused tick (assembly from the 17 qp_former inputs + PDIPM + wrench) under the emulator
+extern "C" int srbd_emul_tick(const double* const* in17, const float* rot, double* const* out6, double* work,
+                              float* wrench, int* iters_done, int B, int num_iters, double tol) {
+  static StageSlot slots[SB_SIZE];
+  static StageSlot fslots[FB_NSLOT];
+  build_stage_slots(slots);
+  build_fast_slots(slots, fslots);
+  PdipmArgs A;
+  for (int i = 0; i < IP_N_IN; ++i) A.in[i] = nullptr;
+  for (int i = 0; i < QP_N_IN; ++i) A.qp_in[i] = in17[i];
+  for (int i = 0; i < IP_N_OUT; ++i) A.out[i] = out6[i];
+  A.work = work; A.iters_done = iters_done; A.num_iters = num_iters; A.tol = tol; A.cold_start = 1;
+  A.fused = 1; A.rot = rot; A.wrench = wrench;
+  g_trace_on = false;
+  for (long long e = 0; e < B; ++e) run_env_fast(A, e, fslots);
   return 0;
 }
 

@@ -92,3 +92,25 @@ def emul_pdipm(qp, iters, x=None, s=None, z=None, y=None, tol=0.0, uniform=True,
     lib.srbd_emul_pdipm(inarr, outarr, work.ctypes.data_as(P), itd.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
                         B, int(iters), ctypes.c_double(tol), int(cold), int(uniform), 0)
     return outs, itd
+
+
+def emul_tick(inputs17, rot, iters, tol=0.0, lane_order=1):
+    """The fused tick (assembly from the 17 qp_former inputs + PDIPM + wrench) of the fast kernel under
+    the CPU warp emulator.  inputs17[1] / [2] may be None.  Returns (outs6, wrench (B,2,6) fp32)."""
+    lib = emul_lib()
+    B = inputs17[0].shape[0]
+    ins = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in inputs17]
+    rot32 = np.ascontiguousarray(rot, dtype=np.float32)
+    outs = [np.zeros((B, n)) for n in (240, 160, 160, 140, 4, 1)]
+    work = np.zeros((B, 1344))
+    wrench = np.zeros((B, 2, 6), np.float32)
+    itd = np.zeros(B, np.int32)
+    P = ctypes.POINTER(ctypes.c_double)
+    inarr = (P * 17)(*[a.ctypes.data_as(P) if a is not None else None for a in ins])
+    outarr = (P * 6)(*[a.ctypes.data_as(P) for a in outs])
+    lib.srbd_emul_set_order(int(lane_order))
+    lib.srbd_emul_tick(inarr, rot32.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), outarr, work.ctypes.data_as(P),
+                       wrench.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), itd.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                       B, int(iters), ctypes.c_double(tol))
+    lib.srbd_emul_set_order(1)
+    return outs, wrench

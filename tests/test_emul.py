@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import biped_pympc_b200 as bp
-from helpers import emul_pdipm, oracle_ip_batch, oracle_qp_batch, rel_err
+from helpers import emul_pdipm, emul_tick, oracle_ip_batch, oracle_qp_batch, rel_err
 from oracle import srbd_oracle as so
 
 TOL_5 = 1e-9      # north_star: fp64 relative error <= 1e-9 on primal/dual solutions
@@ -83,3 +83,27 @@ def test_tolerance_mode_stops_early_and_reports_iterations(qp_small):
         assert np.array_equal(got[i], one[i])
     _, itd = emul_pdipm(qp_small, 7, tol=1e-30)          # never converges -> cap
     assert list(itd) == [7] * 4
+
+
+def test_fused_tick_equals_assembly_then_solve():
+    """The fused tick builds its stage data from the 17 qp_former inputs (no CCS vectors): it must
+    reproduce oracle assembly + kernel solve, with and without an explicit linearisation point, in
+    both lane orders; the wrench is -R' (f, m) per foot with m_x zeroed (mpc_controller_cusadi.py:186-203)."""
+    inp, rot = bp.workload.make_batch(3, seed=21)
+    qp = oracle_qp_batch(inp)
+    two, _ = emul_pdipm(qp, 5)
+    fused, w = emul_tick(inp, rot, 5)
+    for a, b in zip(two, fused):
+        assert rel_err(b, a) < 1e-10          # oracle assembly vs closed forms: 1 ulp in the data, 1e-12 in x
+    inp2 = list(inp); inp2[1] = None; inp2[2] = None
+    fused2, w2 = emul_tick(inp2, rot, 5, lane_order=-1)
+    for a, b in zip(fused, fused2):
+        assert np.array_equal(a, b)
+    assert np.array_equal(w, w2)
+    u0 = fused[0][:, 120:132].astype(np.float32)
+    R = rot.astype(np.float32)
+    for e in range(3):
+        fL, fR, mL, mR = u0[e, 0:3], u0[e, 3:6], u0[e, 6:9].copy(), u0[e, 9:12].copy()
+        mL[0] = 0; mR[0] = 0
+        ref = np.stack([np.concatenate([-R[e].T @ fL, -R[e].T @ mL]), np.concatenate([-R[e].T @ fR, -R[e].T @ mR])])
+        assert np.abs(w[e] - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
