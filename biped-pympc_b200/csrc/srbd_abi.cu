@@ -356,6 +356,7 @@ int srbd_mpc_solve_host(srbd_ctx* c, const double* const* in17_host, const float
   // solve side by side.
   const int per_cta = pdipm_warps_per_cta(true);
   int chunk = (zero_copy ? 147 : 74) * per_cta;     // 2 058 / 1 036 envs
+  if (const char* ev = std::getenv("SRBD_HOST_CHUNK")) chunk = std::atoi(ev) > 0 ? std::atoi(ev) : chunk;   // tuning knob
   if (B <= chunk) chunk = B;
   int rc = SRBD_OK, ci = 0;
   for (int e0 = 0; e0 < B; e0 += chunk, ++ci) {
