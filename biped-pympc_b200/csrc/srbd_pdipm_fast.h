@@ -685,8 +685,17 @@ struct PdipmFast {
         double* ws = gws();
         double* oX = gout(IPO_X, NZ); double* oS = gout(IPO_S, NINEQ); double* oZ = gout(IPO_Z, NINEQ); double* oY = gout(IPO_Y, NEQ);
         double a_new = 0.0;
-        for (int i = lane; i < NZ; i += 32) oX[i] = fma(a_pri, ws[FW_DX + i] + vx[i], oX[i]);
-        for (int i = lane; i < NEQ; i += 32) oY[i] = fma(a_dual, ws[FW_DY + i] + vy[i], oY[i]);
+        {   // all global loads of a lane are issued before the first dependent use (L2 latency once)
+          double xa[8], xo[8], ya[5], yo[5];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) { const int i = lane + 32 * m; const bool on = i < NZ; xa[m] = on ? ws[FW_DX + i] : 0.0; xo[m] = on ? oX[i] : 0.0; }
+#pragma unroll
+          for (int m = 0; m < 5; ++m) { const int i = lane + 32 * m; const bool on = i < NEQ; ya[m] = on ? ws[FW_DY + i] : 0.0; yo[m] = on ? oY[i] : 0.0; }
+#pragma unroll
+          for (int m = 0; m < 8; ++m) { const int i = lane + 32 * m; if (i < NZ) oX[i] = fma(a_pri, xa[m] + vx[i], xo[m]); }
+#pragma unroll
+          for (int m = 0; m < 5; ++m) { const int i = lane + 32 * m; if (i < NEQ) oY[i] = fma(a_dual, ya[m] + vy[i], yo[m]); }
+        }
 #pragma unroll
         for (int t = 0; t < 5; ++t) {
           const int j = 16 * (h ? 9 - t : t) + r;
@@ -725,14 +734,21 @@ struct PdipmFast {
     const double* gF = gin(IP_F, NZ); const double* gB = gin(IP_B, NEQ);
     {
       const double* oX = gout(IPO_X, NZ); const double* oY = gout(IPO_Y, NEQ);
+      double xv[8], yv[5];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) { const int i = lane + 32 * m; xv[m] = i < NZ ? oX[i] : 0.0; }
+#pragma unroll
+      for (int m = 0; m < 5; ++m) { const int i = lane + 32 * m; yv[m] = i < NEQ ? oY[i] : 0.0; }
       int m12 = lane % 12;
-      for (int i = lane; i < NZ; i += 32) {
-        const double v = oX[i];
-        sx[i] = v;
-        if (i < 120) xs[i] = v * (f[FB_HX + m12] + IP_BETA);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int i = lane + 32 * m;
+        if (i < NZ) sx[i] = xv[m];
+        if (i < 120) xs[i] = xv[m] * (f[FB_HX + m12] + IP_BETA);
         m12 += 8; if (m12 >= 12) m12 -= 12;
       }
-      for (int i = lane; i < NEQ; i += 32) sy[i] = oY[i];
+#pragma unroll
+      for (int m = 0; m < 5; ++m) { const int i = lane + 32 * m; if (i < NEQ) sy[i] = yv[m]; }
     }
     w.sync();
     const int jj = r & 7, ft = r >> 3;
