@@ -238,7 +238,7 @@ struct PdipmFast {
     double* f = fb();
     double* V = sm + SM::OFF_P;           // V_COUNT
     double* Wr = V + 232;                 // RW_COUNT
-    qp_value_table(pa->qp_in, e, lane, w, V, Wr);
+    qp_value_table(pa->qp_in, e, lane, 32, w, V, Wr);
     for (int i = lane; i < 168; i += 32) { const int rw = i / 14, c = i - 14 * rw; f[FB_B + i] = c < 12 ? V[V_NBD + 12 * rw + c] : 0.0; }
     if (lane < 12) { f[FB_AB + lane] = V[V_NEG1]; f[FB_HX + lane] = V[V_Q + lane]; f[FB_HU + lane] = V[V_R + lane]; }
     if (lane < 9) f[FB_AB + 12 + lane] = V[V_NADTR + lane];

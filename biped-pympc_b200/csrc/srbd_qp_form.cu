@@ -100,7 +100,7 @@ qp_form_kernel(QpFormArgs a, int B) {
       const long long e = env0 + warp;
       double* V = sV[warp];
       double* W = sRaw[warp];
-      qp_value_table(a.in, e, lane, Warp(), V, W);
+      qp_value_table(a.in, e, lane, 32, Warp(), V, W);
     }
     __syncthreads();
 

@@ -33,30 +33,31 @@ enum : int { RW_RB = 0, RW_IW = 9, RW_BODY = 18, RW_LF = 21, RW_RF = 24, RW_RL =
 
 // V: V_COUNT doubles, W: RW_COUNT doubles of warp-private scratch; in[] = the 17 qp_former inputs
 // (device pointers, env-major); all 32 lanes of the warp must call
-SRBD_DEV void qp_value_table(const double* const* in, long long e, int lane, const Warp& w, double* V, double* W) {
+// `lane` in [0, nl): nl cooperating lanes (32 = a whole warp per env, 16 = half a warp per env)
+SRBD_DEV void qp_value_table(const double* const* in, long long e, int lane0, int nl, const Warp& w, double* V, double* W) {
   // ---- stage raw inputs (nnz order = CasADi column-major) ---------------------------
-  if (lane < 9) { W[RW_RB + lane] = in[IN_RBODY][e * 9 + lane]; W[RW_IW + lane] = in[IN_IWORLD][e * 9 + lane]; }
-  if (lane < 3) {
+  for (int lane = lane0; lane < 9; lane += nl) { W[RW_RB + lane] = in[IN_RBODY][e * 9 + lane]; W[RW_IW + lane] = in[IN_IWORLD][e * 9 + lane]; }
+  for (int lane = lane0; lane < 3; lane += nl) {
     W[RW_BODY + lane] = in[IN_BODY][e * 3 + lane];
     W[RW_LF + lane] = in[IN_LFOOT][e * 3 + lane];
     W[RW_RF + lane] = in[IN_RFOOT][e * 3 + lane];
     W[RW_RL + lane] = in[IN_RESLIN][e * 3 + lane];
     W[RW_RA + lane] = in[IN_RESANG][e * 3 + lane];
   }
-  if (lane < 12) {
+  for (int lane = lane0; lane < 12; lane += nl) {
     W[RW_X0 + lane] = in[IN_X0][e * 12 + lane];
     V[V_Q + lane] = in[IN_Q][e * 12 + lane];
     V[V_R + lane] = in[IN_R][e * 12 + lane];
   }
-  if (lane < 20) W[RW_CT + lane] = in[IN_CONTACT][e * 20 + lane];
-  if (lane == 0) {
+  for (int lane = lane0; lane < 20; lane += nl) W[RW_CT + lane] = in[IN_CONTACT][e * 20 + lane];
+  if (lane0 == 0) {
     W[RW_DT] = in[IN_DT][e]; W[RW_M] = in[IN_M][e]; W[RW_MU] = in[IN_MU][e];
   }
   w.sync();
   const double dt = W[RW_DT], m = W[RW_M], mu = W[RW_MU];
   const double hdt2 = dt * dt / 2;
   // ---- I_world^-1 (adjugate / det); M(i,j) = Iw_flat[i + 3j] ------------------------
-  if (lane < 9) {
+  for (int lane = lane0; lane < 9; lane += nl) {
     const double* M = W + RW_IW;
     auto Mx = [&](int i, int j) { return M[i + 3 * j]; };
     const double det = Mx(0, 0) * (Mx(1, 1) * Mx(2, 2) - Mx(1, 2) * Mx(2, 1))
@@ -68,7 +69,8 @@ SRBD_DEV void qp_value_table(const double* const* in, long long e, int lane, con
   }
   w.sync();
   // ---- angular-acceleration map: I^-1 [skew(rL) | skew(rR) | I | I]   (3 x 12) ------
-  if (lane < 18) {
+  for (int lane = lane0; lane < 27; lane += nl) {
+   if (lane < 18) {
     const int i = lane / 6, c = lane % 6, ft = c / 3, j = c % 3;
     const double* foot = W + (ft == 0 ? RW_LF : RW_RF);
     const double rx = foot[0] - W[RW_BODY + 0], ry = foot[1] - W[RW_BODY + 1], rz = foot[2] - W[RW_BODY + 2];
@@ -78,28 +80,29 @@ SRBD_DEV void qp_value_table(const double* const* in, long long e, int lane, con
     else if (j == 1) v = Ii[2] * rx - Ii[0] * rz;
     else v = Ii[0] * ry - Ii[1] * rx;
     W[RW_BCW + 12 * i + c] = v;
-  } else if (lane < 27) {
+   } else {
     const int i = (lane - 18) / 3, j = (lane - 18) % 3;
     const double v = W[RW_IINV + 3 * i + j];
     W[RW_BCW + 12 * i + 6 + j] = v;
     W[RW_BCW + 12 * i + 9 + j] = v;
+   }
   }
   w.sync();
   // ---- constants, -dt R, contact ----------------------------------------------------
-  if (lane == 0) {
+  if (lane0 == 0) {
     V[V_ZERO] = 0.0; V[V_ONE] = 1.0; V[V_NEG1] = -1.0; V[V_NEGMU] = -mu;
     V[V_NEGLT] = -LT; V[V_NEGLH] = -LH; V[V_NADT] = -dt;
   }
-  if (lane < 9) {   // R(i,j) = Rb_flat[i + 3j]
+  for (int lane = lane0; lane < 9; lane += nl) {   // R(i,j) = Rb_flat[i + 3j]
     const int i = lane / 3, j = lane % 3;
     V[V_NADTR + 3 * i + j] = -(dt * W[RW_RB + i + 3 * j]);
   }
-  if (lane < 20) {  // contact(stage, foot) = flat[stage + 10*foot]; F_max * contact
+  for (int lane = lane0; lane < 20; lane += nl) {  // contact(stage, foot) = flat[stage + 10*foot]; F_max * contact
     const int st = lane % 10, ft = lane / 10;
     V[V_FC + 2 * st + ft] = F_MAX * W[RW_CT + lane];
   }
   // ---- -B_d (12 x 12) ----------------------------------------------------------------
-  for (int idx = lane; idx < 144; idx += 32) {
+  for (int idx = lane0; idx < 144; idx += nl) {
     const int r = idx / 12, c = idx % 12;
     double v = 0.0;
     if (r < 3) {          // euler rows: dt^2/2 * R * Bc_omega
@@ -115,7 +118,7 @@ SRBD_DEV void qp_value_table(const double* const* in, long long e, int lane, con
     V[V_NBD + idx] = -v;
   }
   // ---- c_d and b_0 = c_d + A_d x0 -----------------------------------------------------
-  if (lane < 12) {
+  for (int lane = lane0; lane < 12; lane += nl) {
     const int r = lane, i = r % 3;
     const double* Rb = W + RW_RB;
     const double* x0 = W + RW_X0;

@@ -20,6 +20,7 @@ struct Warp {
   SRBD_DEV double shfl_xor(double v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m); }
   SRBD_DEV double shfl(double v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
   SRBD_DEV int shfl_i(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+  SRBD_DEV bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
 };
 SRBD_DEV double ldg(const double* p) { return __ldg(p); }
 }  // namespace srbd
@@ -116,6 +117,11 @@ struct Warp {
     if (lane_ == 0) st->pub_sel ^= 1;
     sync();
     return r;
+  }
+  bool any(bool p) const {
+    int acc = 0;
+    for (int src = 0; src < WarpEmulState::kLanes; ++src) acc |= shfl_i(p ? 1 : 0, src);
+    return acc != 0;
   }
 };
 inline double ldg(const double* p) { return *p; }

@@ -10,6 +10,7 @@
 
 #include "srbd_stage_table.h"
 #include "srbd_pdipm_fast.h"
+#include "srbd_pdipm_pair.h"
 
 namespace srbd {
 static std::map<std::string, std::vector<double>> g_trace;
@@ -48,6 +49,22 @@ static void run_env_fast(const PdipmArgs& A, long long e, const StageSlot* slots
   });
 }
 
+// two environments per emulated warp (srbd_pdipm_pair.h): envs e0 and e0 + 1 (the second may not exist)
+static void run_env_pair(const PdipmArgs& A, long long e0, int B, const StageSlot* slots) {
+  std::vector<double> smem(2 * FastSmem::SIZE, 0.0);
+  run_warp([&](int lane) {
+    PdipmPair W;
+    W.w.lane_ = lane;
+    const int slot = lane >> 4;
+    long long e = e0 + slot;
+    const bool exists = e < B;
+    if (!exists) e = B - 1;
+    W.sm = smem.data() + slot * FastSmem::SIZE;
+    W.slots = slots;
+    W.run(A, e, exists);
+  }, 1 << 21);
+}
+
 extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, double* work, int* iters_done,
                                int B, int num_iters, double tol, int cold_start, int uniform, int trace) {
   static StageSlot slots[SB_SIZE];
@@ -63,7 +80,8 @@ extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, d
   g_trace_on = trace != 0;
   g_trace.clear();
   for (long long e = 0; e < B; ++e) {
-    if (uniform == 2) run_env_fast(A, e, fslots);
+    if (uniform == 3) { if ((e & 1) == 0) run_env_pair(A, e, B, fslots); }
+    else if (uniform == 2) run_env_fast(A, e, fslots);
     else if (uniform) run_env<true>(A, e, slots, nullptr);
     else run_env<false>(A, e, slots, nullptr);
   }
@@ -72,7 +90,7 @@ extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, d
 
 // fused tick (assembly from the 17 qp_former inputs + PDIPM + wrench) under the emulator
 extern "C" int srbd_emul_tick(const double* const* in17, const float* rot, double* const* out6, double* work,
-                              float* wrench, int* iters_done, int B, int num_iters, double tol) {
+                              float* wrench, int* iters_done, int B, int num_iters, double tol, int pair) {
   static StageSlot slots[SB_SIZE];
   static StageSlot fslots[FB_NSLOT];
   build_stage_slots(slots);
@@ -84,7 +102,8 @@ extern "C" int srbd_emul_tick(const double* const* in17, const float* rot, doubl
   A.work = work; A.iters_done = iters_done; A.num_iters = num_iters; A.tol = tol; A.cold_start = 1;
   A.fused = 1; A.rot = rot; A.wrench = wrench;
   g_trace_on = false;
-  for (long long e = 0; e < B; ++e) run_env_fast(A, e, fslots);
+  if (pair) { for (long long e = 0; e < B; e += 2) run_env_pair(A, e, B, fslots); }
+  else { for (long long e = 0; e < B; ++e) run_env_fast(A, e, fslots); }
   return 0;
 }
 

@@ -71,6 +71,7 @@ def emul_pdipm(qp, iters, x=None, s=None, z=None, y=None, tol=0.0, uniform=True,
     """Runs the PDIPM *device code* under the CPU warp emulator.  Returns (outs6, iters_done).
     uniform: False = general kernel (srbd_pdipm_core.h, arbitrary values on the pattern),
              True / 2 = stage-invariant fast kernel (srbd_pdipm_fast.h),
+             3 = the same mathematics with two environments per warp (srbd_pdipm_pair.h),
              1 = stage-invariant instantiation of the general kernel."""
     if uniform is True:
         uniform = 2
@@ -94,7 +95,7 @@ def emul_pdipm(qp, iters, x=None, s=None, z=None, y=None, tol=0.0, uniform=True,
     return outs, itd
 
 
-def emul_tick(inputs17, rot, iters, tol=0.0, lane_order=1):
+def emul_tick(inputs17, rot, iters, tol=0.0, lane_order=1, pair=False):
     """The fused tick (assembly from the 17 qp_former inputs + PDIPM + wrench) of the fast kernel under
     the CPU warp emulator.  inputs17[1] / [2] may be None.  Returns (outs6, wrench (B,2,6) fp32)."""
     lib = emul_lib()
@@ -111,6 +112,6 @@ def emul_tick(inputs17, rot, iters, tol=0.0, lane_order=1):
     lib.srbd_emul_set_order(int(lane_order))
     lib.srbd_emul_tick(inarr, rot32.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), outarr, work.ctypes.data_as(P),
                        wrench.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), itd.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
-                       B, int(iters), ctypes.c_double(tol))
+                       B, int(iters), ctypes.c_double(tol), int(pair))
     lib.srbd_emul_set_order(1)
     return outs, wrench

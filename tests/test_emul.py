@@ -107,3 +107,17 @@ def test_fused_tick_equals_assembly_then_solve():
         mL[0] = 0; mR[0] = 0
         ref = np.stack([np.concatenate([-R[e].T @ fL, -R[e].T @ mL]), np.concatenate([-R[e].T @ fR, -R[e].T @ mR])])
         assert np.abs(w[e] - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_two_envs_per_warp_mapping_matches_one_env_per_warp(qp_small):
+    """srbd_pdipm_pair.h (experimental mapping, SRBD_PDIPM_PAIR=1): same arithmetic per matrix row, so
+    the iterates are bit-identical after two iterations (only the order of the mu / residual
+    reductions differs); odd batch sizes exercise the read-only shadow slot of the last warp."""
+    a, ia = emul_pdipm([t[:3] for t in qp_small], 2, uniform=2)
+    b, ib = emul_pdipm([t[:3] for t in qp_small], 2, uniform=3)
+    for i in range(4):
+        assert np.array_equal(a[i], b[i])
+    assert rel_err(b[4], a[4]) < 1e-14 and list(ia) == list(ib)
+    c, _ = emul_pdipm([t[:3] for t in qp_small], 2, uniform=3, lane_order=-1)
+    for u, v in zip(b, c):
+        assert np.array_equal(u, v)
