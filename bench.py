@@ -44,8 +44,10 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms from before the warm-up; stop(t0, t1)
+    keeps the samples whose timestamp falls inside the timed region (all of them if the region was
+    shorter than one sampling period, which is then said in the result)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -55,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -64,9 +66,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -74,21 +76,30 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for l in self.lines:
-            p = [x.strip() for x in l.split(",")]
-            if len(p) < 9:
-                continue
-            try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(rows):
+            sm, mx, reasons = [], [], set()
+            for _, l in rows:
+                p = [x.strip() for x in l.split(",")]
+                if len(p) < 10:
+                    continue
+                try:
+                    sm.append(float(p[2])); mx.append(float(p[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[6:10]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+
+        inside = [r for r in self.lines if t0 is not None and t0 <= r[0] <= t1]
+        window = "timed region"
+        if not inside:
+            inside, window = self.lines, "whole run (timed region shorter than one 20 ms sampling period)"
+        sm, mx, reasons = parse(inside)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_reference_run(n_envs, iters, steps, warmup, threads, seed=20261018):
@@ -168,6 +179,8 @@ def run_b200(args):
     def step():
         return ctx.solve(ins, rot_t, num_calls=args.calls, iters_per_call=args.iters, tol=args.tol, iters_done=iters_done)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -177,17 +190,16 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    t_wall0 = time.time()
     for a, b in ev:
         flush.fill_(1.0)           # evict L2 between timed iterations (not timed)
         a.record()
         step()
         b.record()
     barrier()
-    clocks = sampler.stop()
+    t_wall1 = time.time()
     times_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(times_ms)
     if dist is not None:
@@ -216,6 +228,7 @@ def run_b200(args):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1)
     e2e_value = world * B * n_e2e / e2e_s
     h2d = sum(a.numel() * 8 for a in h_in if a is not None) + h_rot.numel() * 4
     d2h = h_w.numel() * 4
@@ -323,8 +336,8 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     # other BASELINE configs (not the default bench line): --calls 4 = the reference tick (4 x 5 iterations,
