@@ -301,7 +301,7 @@ def run_b200(args):
                             "achieved": ach, "peak": dfma,
                             "unit": "TFLOP/s", "frac": ach / dfma, "traffic": traffic,
                             "traffic_note": "DRAM bytes per launch from the committed ncu capture "
-                                            f"({cap.get('capture')}); algorithmic I/O is 29 288 B/env = {29288 * B} B: "
+                                            f"({cap.get('capture')}); algorithmic I/O of the fused tick is 1 696 B of inputs + 5 640 B of iterates + 48 B of wrench per env = {7384 * B} B: "
                                             "the kernel is bound by the FP64 pipe and shared-memory bandwidth, not HBM",
                             "smem_wavefronts_per_sm_cycle_ncu": cap.get("smem_wavefronts_per_sm_cycle"),
                             "kernel_ms": pd_ms, "share_of_step": pd_ms / (total_ms / args.steps) if world == 1 else None,
