@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "srbd_version", "srbd_error_string", "srbd_last_cuda_error", "srbd_init",
     "srbd_qp_former_nnz_in", "srbd_qp_former_nnz_out", "srbd_pdipm_nnz_in", "srbd_pdipm_nnz_out",
     "srbd_pattern", "srbd_qp_form", "srbd_pdipm_work_doubles", "srbd_pdipm", "srbd_pdipm_is_stage_invariant", "srbd_wrench",
-    "srbd_ctx_create", "srbd_ctx_destroy", "srbd_mpc_solve", "srbd_mpc_solve_host",
+    "srbd_ctx_create", "srbd_ctx_destroy", "srbd_mpc_solve", "srbd_mpc_solve_warm", "srbd_mpc_solve_host",
     "srbd_qp_former_evaluate", "srbd_sparse_pdipm_multiple_iterations_evaluate", "srbd_dfma_peak",
 )
 
@@ -65,6 +65,7 @@ def load(build_if_missing: bool = True):
     lib.srbd_ctx_create.argtypes = [ctypes.POINTER(vp), ci, ci]
     lib.srbd_ctx_destroy.argtypes = [vp]
     lib.srbd_mpc_solve.argtypes = [vp, vp, vp, ci, ci, ci, cd, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.srbd_mpc_solve_warm.argtypes = [vp, vp, vp, ci, ci, cd, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.srbd_mpc_solve_host.argtypes = [vp, vp, vp, ci, ci, ci, cd, vp, vp, vp]
     lib.srbd_qp_former_evaluate.restype = ctypes.c_float
     lib.srbd_qp_former_evaluate.argtypes = [vp, vp, vp, ci]
@@ -232,6 +233,31 @@ class Context:
             check(lib.srbd_mpc_solve(self._h, _ptr_array(ins), ptr(rot), B, int(num_calls), int(iters_per_call),
                                      float(tol), ptr(w), *[ptr(t) for t in extra], ptr(iters_done), _stream()))
         return (w, *extra) if want_iterates else w
+
+    def solve_warm(self, inputs17, rotation_body, iters=20, tol=0.0, reset=None, want_iterates=False):
+        """EXTENSION (the reference cold-starts every tick): one tick warm-started from the (x, y) this
+        context found at its previous solve_warm call; s = max(h - G x, 1) and z = 1 are re-initialised.
+        The first call is a cold start.  reset: optional int32 (B,) device tensor, nonzero = cold-start
+        that env (episode reset).  inputs17[1] / [2] may be None.  Returns like solve()."""
+        import torch
+        lib = load()
+        keep = [i for i in range(len(QP_NNZ_IN)) if i not in (1, 2) or inputs17[i] is not None]
+        chk, B = _check_inputs([inputs17[i] for i in keep], [QP_NNZ_IN[i] for i in keep])
+        ins = [None] * len(QP_NNZ_IN)
+        for i, t in zip(keep, chk):
+            ins[i] = t
+        dev = chk[0].device
+        rot = rotation_body.to(torch.float32).contiguous()
+        w = torch.empty((B, 2, 6), dtype=torch.float32, device=dev)
+        if getattr(self, "_warm", None) is None:
+            self._warm = [torch.zeros((self.max_B, n), dtype=torch.float64, device=dev) for n in (240, 160, 160, 140, 4)]
+            reset = torch.ones(B, dtype=torch.int32, device=dev)        # nothing to start from yet
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        x, s_, z, y, res = self._warm
+        with torch.cuda.device(dev):
+            check(lib.srbd_mpc_solve_warm(self._h, _ptr_array(ins, allow_none=True), ptr(rot), B, int(iters), float(tol),
+                                          ptr(reset), ptr(w), ptr(x), ptr(s_), ptr(z), ptr(y), ptr(res), None, _stream()))
+        return (w, x[:B], s_[:B], z[:B], y[:B], res[:B]) if want_iterates else w
 
     def solve_host(self, inputs17_host, rotation_body_host, wrench_host, num_calls=1, iters_per_call=5, tol=0.0,
                    x_out_host=None, res_out_host=None):

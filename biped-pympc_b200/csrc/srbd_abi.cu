@@ -107,6 +107,7 @@ struct srbd_ctx {
   cudaStream_t stream = nullptr;          // used by the host entry (chunks alternate between
   cudaStream_t stream2 = nullptr;         // the two streams so that copies overlap the solve)
   cudaEvent_t done2 = nullptr;
+  int have_prev = 0;                      // envs whose (x, y) of the previous srbd_mpc_solve_warm are in it[]
   bool unfused = false;                   // SRBD_TICK_UNFUSED=1: assembly, solve and wrench as three launches
 };
 
@@ -184,7 +185,7 @@ int srbd_pdipm(const double* const* in10, double* const* out6, double* work, int
   }
   for (int i = 0; i < IP_N_OUT; ++i) { if (!out6[i]) return SRBD_EINVAL; a.out[i] = out6[i]; }
   a.work = work; a.iters_done = iters_done; a.num_iters = num_iters; a.tol = tol; a.cold_start = cold ? 1 : 0;
-  a.fused = 0; a.rot = nullptr; a.wrench = nullptr;
+  a.fused = 0; a.rot = nullptr; a.wrench = nullptr; a.warm_xy = 0; a.reset = nullptr;
   for (int i = 0; i < QP_N_IN; ++i) a.qp_in[i] = nullptr;
   SRBD_CUDA(launch_pdipm(a, B, (flags & SRBD_STAGE_INVARIANT) != 0, num_sms(), (cudaStream_t)stream));
   return SRBD_OK;
@@ -269,14 +270,15 @@ namespace {
 // already point at env0
 int solve_range(srbd_ctx* c, const double* const* in17, const float* rotation_body, int env0, int B,
                 int iters, double tol, float* wrench, double* x_out, double* s_out, double* z_out,
-                double* y_out, double* res_out, int* iters_done, cudaStream_t st) {
+                double* y_out, double* res_out, int* iters_done, cudaStream_t st,
+                bool warm = false, const int* reset = nullptr) {
   const size_t o = (size_t)env0;
   double* x = x_out ? x_out : c->it[0] + o * NZ;
   double* s = s_out ? s_out : c->it[1] + o * NINEQ;
   double* z = z_out ? z_out : c->it[2] + o * NINEQ;
   double* y = y_out ? y_out : c->it[3] + o * NEQ;
   double* res = res_out ? res_out : c->res + o * 4;
-  if (!c->unfused) {
+  if (!c->unfused || warm) {
     // ONE launch: the PDIPM kernel assembles its stage data from the 17 inputs (no CCS round trip
     // through HBM), iterates, and writes the wrench
     int rc = ensure_init();
@@ -290,6 +292,7 @@ int solve_range(srbd_ctx* c, const double* const* in17, const float* rotation_bo
     a.out[IPO_X] = x; a.out[IPO_S] = s; a.out[IPO_Z] = z; a.out[IPO_Y] = y; a.out[IPO_RES] = res; a.out[IPO_MU] = c->mu + o;
     a.work = c->work + o * PDIPM_WORK_DOUBLES; a.iters_done = iters_done; a.num_iters = iters; a.tol = tol;
     a.cold_start = 1; a.fused = 1; a.rot = rotation_body; a.wrench = wrench;
+    a.warm_xy = warm ? 1 : 0; a.reset = reset;
     SRBD_CUDA(launch_pdipm(a, B, true, num_sms(), st));
     return SRBD_OK;
   }
@@ -322,6 +325,21 @@ int srbd_mpc_solve(srbd_ctx* c, const double* const* in17, const float* rotation
   // one call with num_calls*iters_per_call iterations, which is what is launched here.
   return solve_range(c, in17, rotation_body, 0, B, num_calls * iters_per_call, tol, wrench, x_out, s_out, z_out,
                      y_out, res_out, iters_done, (cudaStream_t)stream);
+}
+
+int srbd_mpc_solve_warm(srbd_ctx* c, const double* const* in17, const float* rotation_body, int B,
+                        int iters, double tol, const int* reset, float* wrench, double* x_io, double* s_out,
+                        double* z_out, double* y_io, double* res_out, int* iters_done, void* stream) {
+  if (!c || !in17 || B < 0 || B > c->max_B || iters < 0) return SRBD_EINVAL;
+  if (wrench && !rotation_body) return SRBD_EINVAL;
+  if ((x_io == nullptr) != (y_io == nullptr)) return SRBD_EINVAL;
+  if (B == 0) return SRBD_OK;
+  // with the context's own buffers the first call has nothing to start from: it is a cold start
+  const bool warm = (x_io != nullptr) || c->have_prev >= B;
+  int rc = solve_range(c, in17, rotation_body, 0, B, iters, tol, wrench, x_io, s_out, z_out, y_io, res_out, iters_done,
+                       (cudaStream_t)stream, warm, warm ? reset : nullptr);
+  if (rc == SRBD_OK && !x_io) c->have_prev = B;
+  return rc;
 }
 
 int srbd_mpc_solve_host(srbd_ctx* c, const double* const* in17_host, const float* rotation_body_host,

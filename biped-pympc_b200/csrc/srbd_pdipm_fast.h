@@ -585,10 +585,13 @@ struct PdipmFast {
     lane = w.lane(); h = lane >> 4; r = lane & 15; rr = r < 12 ? r : 11;
     {
       double* oX = gout(IPO_X, NZ); double* oS = gout(IPO_S, NINEQ); double* oZ = gout(IPO_Z, NINEQ); double* oY = gout(IPO_Y, NEQ);
+      const bool keep_xy = A.cold_start && A.warm_xy && !(A.reset && A.reset[e] != 0);
       if (A.cold_start) {
-        for (int i = lane; i < NZ; i += 32) oX[i] = 0.0;
+        if (!keep_xy) {
+          for (int i = lane; i < NZ; i += 32) oX[i] = 0.0;
+          for (int i = lane; i < NEQ; i += 32) oY[i] = 1.0;
+        }
         for (int i = lane; i < NINEQ; i += 32) oZ[i] = 1.0;
-        for (int i = lane; i < NEQ; i += 32) oY[i] = 1.0;
       } else {
         const double* ix = gin(IP_X, NZ); const double* is = gin(IP_S, NINEQ);
         const double* iz = gin(IP_Z, NINEQ); const double* iy = gin(IP_Y, NEQ);
@@ -608,9 +611,15 @@ struct PdipmFast {
         }
         return -1;
       }
-      if (A.cold_start) {   // s = max(h, 1); in fused mode h only exists after the set-up
+      if (A.cold_start) {   // s = max(h - G x, 1) (x = 0 unless warm); in fused mode h only exists after the set-up
+        const double* f = fb();
+        const double ga = f[goa], gb = f[gob];
 #pragma unroll
-        for (int t = 0; t < 5; ++t) { const int k = h ? 9 - t : t, j = 16 * k + r; oS[j] = fmax(h_of(k, j), 1.0); }
+        for (int t = 0; t < 5; ++t) {
+          const int k = h ? 9 - t : t, j = 16 * k + r;
+          const double gx = keep_xy ? ga * oX[120 + 12 * k + ca] + gb * oX[120 + 12 * k + cz] : 0.0;
+          oS[j] = fmax(h_of(k, j) - gx, 1.0);
+        }
       }
       w.sync();
     }

@@ -729,11 +729,14 @@ struct PdipmPair {
     pa = &A; e = env;
     lane = w.lane(); l16 = lane & 15; l = lane & 7; h = (lane >> 3) & 1; own = l < 6; wr = exists;
     double* oX = gout(IPO_X, NZ); double* oS = gout(IPO_S, NINEQ); double* oZ = gout(IPO_Z, NINEQ); double* oY = gout(IPO_Y, NEQ);
+    const bool keep_xy = A.cold_start && A.warm_xy && !(A.reset && A.reset[e] != 0);
     if (exists) {
       if (A.cold_start) {
-        for (int i = l16; i < NZ; i += 16) oX[i] = 0.0;
+        if (!keep_xy) {
+          for (int i = l16; i < NZ; i += 16) oX[i] = 0.0;
+          for (int i = l16; i < NEQ; i += 16) oY[i] = 1.0;
+        }
         for (int i = l16; i < NINEQ; i += 16) oZ[i] = 1.0;
-        for (int i = l16; i < NEQ; i += 16) oY[i] = 1.0;
       } else {
         const double* ix = gin(IP_X, NZ); const double* is = gin(IP_S, NINEQ);
         const double* iz = gin(IP_Z, NINEQ); const double* iy = gin(IP_Y, NEQ);
@@ -761,7 +764,11 @@ struct PdipmPair {
 #pragma unroll
       for (int t = 0; t < 5; ++t)
 #pragma unroll
-        for (int q = 0; q < 2; ++q) { const int k = h ? 9 - t : t, j = 16 * k + 8 * q + l; oS[j] = fmax(h_of(k, j), 1.0); }
+        for (int q = 0; q < 2; ++q) {
+          const int k = h ? 9 - t : t, j = 16 * k + 8 * q + l;
+          const double gx = keep_xy ? fb()[Q[q].goa] * oX[120 + 12 * k + Q[q].ca] + fb()[Q[q].gob] * oX[120 + 12 * k + Q[q].cz] : 0.0;
+          oS[j] = fmax(h_of(k, j) - gx, 1.0);
+        }
     }
     w.sync();
 

@@ -118,6 +118,16 @@ int srbd_mpc_solve(srbd_ctx* ctx, const double* const* in17, const float* rotati
                    int num_calls, int iters_per_call, double tol,
                    float* wrench, double* x_out, double* s_out, double* z_out, double* y_out,
                    double* res_out, int* iters_done, void* stream);
+/* EXTENSION (not in the reference, which cold-starts every tick): the same tick warm-started from the
+ * previous tick's primal / equality-dual solution.  (x, y) are kept, s = max(h - G x, 1) and z = 1
+ * are re-initialised as in the cold start; in the closed-loop rollouts of tools/closed_loop.py 20
+ * warm iterations per tick do what 30 cold ones do.  x_io / y_io: device buffers holding the previous
+ * solution on entry and the new one on return, or both NULL = the context's own buffers (whose first
+ * call is then a cold start).  reset: optional device int[B]; envs with reset[e] != 0 (episode
+ * resets) are cold-started.  `iters` Newton iterations in one launch. */
+int srbd_mpc_solve_warm(srbd_ctx* ctx, const double* const* in17, const float* rotation_body, int B,
+                        int iters, double tol, const int* reset, float* wrench, double* x_io, double* s_out,
+                        double* z_out, double* y_io, double* res_out, int* iters_done, void* stream);
 /* the same with HOST buffers, synchronous.  Page-locked (pinned) buffers are read and written in
  * place over PCIe by the kernels (UVA mapping); pageable ones are staged with cudaMemcpyAsync.  The
  * batch is cut into chunks that alternate between two internal streams so that the input traffic

@@ -75,7 +75,7 @@ extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, d
   for (int i = 0; i < IP_N_IN; ++i) A.in[i] = in10[i];
   for (int i = 0; i < IP_N_OUT; ++i) A.out[i] = out6[i];
   A.work = work; A.iters_done = iters_done; A.num_iters = num_iters; A.tol = tol; A.cold_start = cold_start;
-  A.fused = 0; A.rot = nullptr; A.wrench = nullptr;
+  A.fused = 0; A.rot = nullptr; A.wrench = nullptr; A.warm_xy = 0; A.reset = nullptr;
   for (int i = 0; i < QP_N_IN; ++i) A.qp_in[i] = nullptr;
   g_trace_on = trace != 0;
   g_trace.clear();
@@ -90,7 +90,8 @@ extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, d
 
 // fused tick (assembly from the 17 qp_former inputs + PDIPM + wrench) under the emulator
 extern "C" int srbd_emul_tick(const double* const* in17, const float* rot, double* const* out6, double* work,
-                              float* wrench, int* iters_done, int B, int num_iters, double tol, int pair) {
+                              float* wrench, int* iters_done, int B, int num_iters, double tol, int pair,
+                              int warm, const int* reset) {
   static StageSlot slots[SB_SIZE];
   static StageSlot fslots[FB_NSLOT];
   build_stage_slots(slots);
@@ -100,7 +101,7 @@ extern "C" int srbd_emul_tick(const double* const* in17, const float* rot, doubl
   for (int i = 0; i < QP_N_IN; ++i) A.qp_in[i] = in17[i];
   for (int i = 0; i < IP_N_OUT; ++i) A.out[i] = out6[i];
   A.work = work; A.iters_done = iters_done; A.num_iters = num_iters; A.tol = tol; A.cold_start = 1;
-  A.fused = 1; A.rot = rot; A.wrench = wrench;
+  A.fused = 1; A.rot = rot; A.wrench = wrench; A.warm_xy = warm; A.reset = reset;
   g_trace_on = false;
   if (pair) { for (long long e = 0; e < B; e += 2) run_env_pair(A, e, B, fslots); }
   else { for (long long e = 0; e < B; ++e) run_env_fast(A, e, fslots); }

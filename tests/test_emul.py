@@ -127,3 +127,22 @@ def test_two_envs_per_warp_mapping_matches_one_env_per_warp(qp_small):
     c5, _ = emul_pdipm(qp3, 5, uniform=3, lane_order=-1)
     for u, v in zip(b5, c5):
         assert np.array_equal(u, v)
+
+
+def test_warm_start_semantics():
+    """warm_xy keeps (x, y) of the output buffers and re-initialises s = max(h - G x, 1), z = 1; envs
+    flagged in `reset` are cold-started (bit-identical to the cold tick)."""
+    from oracle import srbd_oracle as so
+    inp, rot = bp.workload.make_batch(3, seed=21)
+    cold, _ = emul_tick(inp, rot, 5)
+    again, _ = emul_tick(inp, rot, 5, warm_from=(cold[0], cold[3]), reset=[1, 1, 1])
+    for u, v in zip(again, cold):
+        assert np.array_equal(u, v)
+    warm, _ = emul_tick(inp, rot, 5, warm_from=(cold[0], cold[3]), reset=[0, 1, 0])
+    qp = oracle_qp_batch(inp)
+    Gd = [so.dense_from_ccs(qp[4][e], so.G_COLPTR, so.G_ROW, (160, 240)) for e in range(3)]
+    s0 = np.stack([np.maximum(qp[5][e] - Gd[e] @ cold[0][e], 1.0) for e in range(3)])
+    ref, _ = emul_pdipm(qp, 5, x=cold[0], s=s0, z=np.ones_like(s0), y=cold[3])
+    for i in range(4):
+        assert np.array_equal(warm[i][1], cold[i][1])
+        assert rel_err(warm[i][[0, 2]], ref[i][[0, 2]]) < 1e-10
