@@ -82,3 +82,25 @@ def test_config1_single_t1_standing_oracles_agree():
     u0 = l20[0][0, 120:132]
     # left / right symmetric; the first-stage vertical force is the weight plus the tracking correction
     assert abs(u0[2] - u0[5]) < 1e-4 * abs(u0[2]) and abs(u0[2] + u0[5] - 40.0 * 9.81) < 0.15 * 40.0 * 9.81
+
+
+def test_pdipm_converges_to_the_kkt_point_of_the_qp():
+    """Independent of any restated solver: a convex QP's KKT conditions are necessary and sufficient.
+    On BASELINE config 1 the iterates of the reference algorithm (C oracle, and the kernel code under the
+    emulator) reach a point that satisfies them on the qp_former data itself -- stationarity, primal
+    feasibility, dual feasibility, complementarity (limited by the 1e-8 clamps and the beta / delta
+    regularisation of sparse_pdipm_solver.py:416-439,511-515)."""
+    from helpers import emul_pdipm
+    inp = bp.workload.config1_t1_standing()
+    qp = co.qp_former(inp)
+    Hv, f, Av, b, Gv, d = [a[0] for a in qp]
+    A = so.dense_from_ccs(Av, so.A_COLPTR, so.A_ROW, (140, 240))
+    G = so.dense_from_ccs(Gv, so.G_COLPTR, so.G_ROW, (160, 240))
+    for outs in (co.pdipm(qp, 60), emul_pdipm(qp, 60)[0]):
+        x, s, z, y = [a[0] for a in outs[:4]]
+        assert np.abs(Hv * x + f + G.T @ z + A.T @ y).max() < 1e-5          # stationarity
+        assert np.abs(A @ x - b).max() < 1e-9                               # equalities
+        assert (G @ x - d).max() < 1e-7 and z.min() >= 0                    # inequalities, dual sign
+        assert np.abs(z * (d - G @ x)).max() < 1e-4                         # complementarity
+    # and the optimum carries the weight: sum of vertical forces of stage 0 within 15 % of m g
+    assert abs(x[122] + x[125] - 40.0 * 9.81) < 0.15 * 40.0 * 9.81
