@@ -7,7 +7,7 @@ Drop-in for the hot path of rl-augmented-mpc/Biped-PyMPC: the two CusADi functio
 The directory name contains a hyphen; import it through the ``biped_pympc_b200`` shim at
 the repository root (``import biped_pympc_b200 as bp``)."""
 from . import _native, workload  # noqa: F401
-from ._native import (COLD_START, STAGE_INVARIANT, Context, SrbdError, dfma_peak, is_stage_invariant, pattern,  # noqa: F401
+from ._native import (COLD_START, STAGE_INVARIANT, Context, SrbdError, dfma_peak, is_stage_invariant, marshal, pattern,  # noqa: F401
                       pdipm, qp_form, wrench)
 from .cusadi_function import B200Function, PDIPM_FUNCTION, QP_FORMER_FUNCTION  # noqa: F401
 from .mpc_controller_b200 import MPCControllerB200, solve_tick  # noqa: F401

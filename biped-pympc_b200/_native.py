@@ -27,7 +27,7 @@ _PP = ctypes.POINTER(_P)
 EXPORTED_SYMBOLS = (
     "srbd_version", "srbd_error_string", "srbd_last_cuda_error", "srbd_init",
     "srbd_qp_former_nnz_in", "srbd_qp_former_nnz_out", "srbd_pdipm_nnz_in", "srbd_pdipm_nnz_out",
-    "srbd_pattern", "srbd_qp_form", "srbd_pdipm_work_doubles", "srbd_pdipm", "srbd_pdipm_is_stage_invariant", "srbd_wrench",
+    "srbd_pattern", "srbd_marshal_inputs", "srbd_qp_form", "srbd_pdipm_work_doubles", "srbd_pdipm", "srbd_pdipm_is_stage_invariant", "srbd_wrench",
     "srbd_ctx_create", "srbd_ctx_destroy", "srbd_mpc_solve", "srbd_mpc_solve_warm", "srbd_mpc_solve_host",
     "srbd_qp_former_evaluate", "srbd_sparse_pdipm_multiple_iterations_evaluate", "srbd_dfma_peak",
 )
@@ -61,6 +61,7 @@ def load(build_if_missing: bool = True):
     lib.srbd_pdipm_work_doubles.argtypes = [ci]
     lib.srbd_pdipm.argtypes = [vp, vp, vp, vp, ci, ci, cd, cu, vp]
     lib.srbd_pdipm_is_stage_invariant.argtypes = [vp, ci, vp, ctypes.POINTER(ci)]
+    lib.srbd_marshal_inputs.argtypes = [vp, ci, ci, ci, cd, cd, vp, ci, vp]
     lib.srbd_wrench.argtypes = [vp, vp, vp, ci, vp]
     lib.srbd_ctx_create.argtypes = [ctypes.POINTER(vp), ci, ci]
     lib.srbd_ctx_destroy.argtypes = [vp]
@@ -144,6 +145,30 @@ def qp_form(inputs: Sequence, out: Optional[List] = None) -> List:
     return out
 
 
+def marshal(f32_tensors: Sequence, mass: float, mu: float, fix_layout=False, q_stride_bug=False, out=None,
+            with_linearisation_point=True) -> List:
+    """mpc_controller_cusadi.py:54-95 in one launch: 12 fp32 device tensors (x0, x_ref, R_body, I_world,
+    root_position, foot_position, contact_table, dt_mpc, Q, R, residual_lin_accel, residual_ang_accel)
+    -> the 17 fp64 (B, nnz) qp_former inputs (entries 1, 2 are None unless with_linearisation_point)."""
+    import torch
+    lib = load()
+    ts = []
+    for i, t in enumerate(f32_tensors):
+        if t.dtype != torch.float32 or t.device.type != "cuda":
+            raise TypeError(f"marshal: argument {i} must be a float32 CUDA tensor")
+        ts.append(t.contiguous())
+    if len(ts) != 12:
+        raise ValueError("marshal: expected 12 tensors")
+    B, dev = ts[0].shape[0], ts[0].device
+    if out is None:
+        out = [torch.empty((B, n), dtype=torch.float64, device=dev) if (with_linearisation_point or i not in (1, 2)) else None
+               for i, n in enumerate(QP_NNZ_IN)]
+    with torch.cuda.device(dev):
+        check(lib.srbd_marshal_inputs(_ptr_array(ts), int(ts[8].numel()), int(bool(fix_layout)), int(bool(q_stride_bug)),
+                                      float(mass), float(mu), _ptr_array(out, allow_none=True), B, _stream()))
+    return out
+
+
 def is_stage_invariant(inputs: Sequence) -> bool:
     """Synchronous probe: True when [Q_val, G_val, A_val, ...] is qp_former-shaped for every env
     (identical stage blocks, unit coefficients on x_{k+1} / Mx rows), i.e. the fast kernel applies."""
@@ -196,6 +221,16 @@ def wrench(x_sol, rotation_body):
     return out
 
 
+def _check_qp_inputs(inputs17):
+    """_check_inputs for the 17 qp_former inputs; entries 1, 2 (x, u) may be None = all ones."""
+    keep = [i for i in range(len(QP_NNZ_IN)) if i not in (1, 2) or inputs17[i] is not None]
+    chk, B = _check_inputs([inputs17[i] for i in keep], [QP_NNZ_IN[i] for i in keep])
+    ins = [None] * len(QP_NNZ_IN)
+    for i, t in zip(keep, chk):
+        ins[i] = t
+    return ins, B, chk[0].device
+
+
 class Context:
     """Library-owned workspace for the fused tick (srbd_ctx_*)."""
 
@@ -221,8 +256,7 @@ class Context:
         """Device tensors in -> (wrench (B,2,6) fp32[, x, s, z, y, res])."""
         import torch
         lib = load()
-        ins, B = _check_inputs(inputs17, QP_NNZ_IN)
-        dev = ins[0].device
+        ins, B, dev = _check_qp_inputs(inputs17)
         rot = rotation_body.to(torch.float32).contiguous()
         w = torch.empty((B, 2, 6), dtype=torch.float32, device=dev)
         extra = [None] * 5
@@ -230,7 +264,7 @@ class Context:
             extra = [torch.empty((B, n), dtype=torch.float64, device=dev) for n in (240, 160, 160, 140, 4)]
         ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
         with torch.cuda.device(dev):
-            check(lib.srbd_mpc_solve(self._h, _ptr_array(ins), ptr(rot), B, int(num_calls), int(iters_per_call),
+            check(lib.srbd_mpc_solve(self._h, _ptr_array(ins, allow_none=True), ptr(rot), B, int(num_calls), int(iters_per_call),
                                      float(tol), ptr(w), *[ptr(t) for t in extra], ptr(iters_done), _stream()))
         return (w, *extra) if want_iterates else w
 
@@ -241,12 +275,7 @@ class Context:
         that env (episode reset).  inputs17[1] / [2] may be None.  Returns like solve()."""
         import torch
         lib = load()
-        keep = [i for i in range(len(QP_NNZ_IN)) if i not in (1, 2) or inputs17[i] is not None]
-        chk, B = _check_inputs([inputs17[i] for i in keep], [QP_NNZ_IN[i] for i in keep])
-        ins = [None] * len(QP_NNZ_IN)
-        for i, t in zip(keep, chk):
-            ins[i] = t
-        dev = chk[0].device
+        ins, B, dev = _check_qp_inputs(inputs17)
         rot = rotation_body.to(torch.float32).contiguous()
         w = torch.empty((B, 2, 6), dtype=torch.float32, device=dev)
         if getattr(self, "_warm", None) is None:

@@ -211,6 +211,16 @@ int srbd_pdipm_is_stage_invariant(const double* const* in10, int B, void* stream
   return SRBD_OK;
 }
 
+int srbd_marshal_inputs(const float* const* f32in12, int nQ, int fix_layout, int q_stride_bug, double mass, double mu,
+                        double* const* out17, int B, void* stream) {
+  if (!f32in12 || !out17 || B < 0 || nQ < 12) return SRBD_EINVAL;
+  for (int i = 0; i < 12; ++i) if (!f32in12[i]) return SRBD_EINVAL;
+  for (int i = 0; i < QP_N_IN; ++i) if (!out17[i] && i != IN_X && i != IN_U) return SRBD_EINVAL;
+  if (B == 0) return SRBD_OK;
+  SRBD_CUDA(launch_marshal(f32in12, nQ, fix_layout, q_stride_bug, mass, mu, out17, B, (cudaStream_t)stream));
+  return SRBD_OK;
+}
+
 int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, int B, void* stream) {
   if (!x_sol || !rotation_body || !wrench || B < 0) return SRBD_EINVAL;
   SRBD_CUDA(launch_wrench(x_sol, rotation_body, wrench, B, (cudaStream_t)stream));

@@ -21,6 +21,9 @@ cudaError_t launch_wrench(const double* x_sol, const float* rotation_body_rowmaj
 // *flag |= 1 unless every env carries stage-invariant, unit-E data (what qp_former produces)
 cudaError_t launch_stage_invariant_probe(const double* Q, const double* G, const double* A, int* flag, int B,
                                          cudaStream_t stream);
+// controller state (fp32) -> the qp_former inputs (fp64), mpc_controller_cusadi.py:54-95
+cudaError_t launch_marshal(const float* const* f32in12, int nQ, int fix_layout, int q_stride_bug, double mass, double mu,
+                           double* const* out17, int B, cudaStream_t stream);
 // DFMA micro-benchmark used for the FP64 roofline denominator
 cudaError_t launch_dfma_peak(double* sink, int iters, int blocks, int threads, cudaStream_t stream);
 

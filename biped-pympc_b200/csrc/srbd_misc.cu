@@ -57,6 +57,69 @@ cudaError_t launch_stage_invariant_probe(const double* Q, const double* G, const
   return cudaGetLastError();
 }
 
+// Input builder: the marshalling of mpc_controller_cusadi.py:54-95 (casts to fp64, flattening,
+// per-env replication of the constants) as one launch instead of ~25 small torch kernels.  One warp per
+// env.  Bit-exact: every output is an fp32 -> fp64 cast of one controller value.  Layout switches
+// follow SURVEY.md 8b: fix_layout = 0 reproduces the reference's row-major flattening of R_body and of
+// the (10,2) contact table into buffers the kernels read column-major (Q1, Q2); q_stride_bug = 1
+// reproduces the 13-long Q strided by 12 (Q3).
+struct MarshalArgs {
+  const float *x0, *x_ref, *R_body, *I_world, *root_pos, *foot_pos, *contact, *dt_mpc, *Q, *R, *res_lin, *res_ang;
+  int nQ, fix_layout, q_stride_bug;
+  double mass, mu;
+  double* out[QP_N_IN];   // out[IN_X] / out[IN_U] may be null (not written: the kernels treat null as ones)
+};
+__global__ void marshal_kernel(MarshalArgs a, int B) {
+  const long long e = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (e >= B) return;
+  for (int i = lane; i < 120; i += 32) {
+    a.out[IN_XREF][e * 120 + i] = (double)a.x_ref[e * 120 + i];
+    if (a.out[IN_X]) a.out[IN_X][e * 120 + i] = 1.0;
+    if (a.out[IN_U]) a.out[IN_U][e * 120 + i] = 1.0;
+  }
+  if (lane < 12) {
+    a.out[IN_X0][e * 12 + lane] = (double)a.x0[e * 12 + lane];
+    const long long qi = a.q_stride_bug ? (e * 12 + lane) % a.nQ : lane;     // Q3: env e reads Qflat[12e + i]
+    a.out[IN_Q][e * 12 + lane] = (double)a.Q[qi];
+    a.out[IN_R][e * 12 + lane] = (double)a.R[lane];
+  }
+  if (lane < 9) {   // flat[k]: fix_layout ? column-major nnz order of the true matrix : row-major as is
+    const int src = a.fix_layout ? (lane % 3) * 3 + lane / 3 : lane;
+    a.out[IN_RBODY][e * 9 + lane] = (double)a.R_body[e * 9 + src];
+    a.out[IN_IWORLD][e * 9 + lane] = (double)a.I_world[e * 9 + src];
+  }
+  if (lane < 20) {  // contact (10,2) row-major; fix_layout: flat[k] = contact[k % 10, k / 10]
+    const int src = a.fix_layout ? (lane % 10) * 2 + lane / 10 : lane;
+    a.out[IN_CONTACT][e * 20 + lane] = (double)a.contact[e * 20 + src];
+  }
+  if (lane < 3) {
+    a.out[IN_BODY][e * 3 + lane] = (double)a.root_pos[e * 3 + lane];
+    a.out[IN_LFOOT][e * 3 + lane] = (double)a.foot_pos[e * 6 + lane];
+    a.out[IN_RFOOT][e * 3 + lane] = (double)a.foot_pos[e * 6 + 3 + lane];
+    a.out[IN_RESLIN][e * 3 + lane] = (double)a.res_lin[e * 3 + lane];
+    a.out[IN_RESANG][e * 3 + lane] = (double)a.res_ang[e * 3 + lane];
+  }
+  if (lane == 0) {
+    a.out[IN_DT][e] = (double)a.dt_mpc[e];
+    a.out[IN_M][e] = a.mass;
+    a.out[IN_MU][e] = a.mu;
+  }
+}
+
+cudaError_t launch_marshal(const float* const* f32in12, int nQ, int fix_layout, int q_stride_bug, double mass, double mu,
+                           double* const* out17, int B, cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  MarshalArgs a;
+  a.x0 = f32in12[0]; a.x_ref = f32in12[1]; a.R_body = f32in12[2]; a.I_world = f32in12[3]; a.root_pos = f32in12[4];
+  a.foot_pos = f32in12[5]; a.contact = f32in12[6]; a.dt_mpc = f32in12[7]; a.Q = f32in12[8]; a.R = f32in12[9];
+  a.res_lin = f32in12[10]; a.res_ang = f32in12[11];
+  a.nQ = nQ; a.fix_layout = fix_layout; a.q_stride_bug = q_stride_bug; a.mass = mass; a.mu = mu;
+  for (int i = 0; i < QP_N_IN; ++i) a.out[i] = out17[i];
+  marshal_kernel<<<(B + 3) / 4, 128, 0, stream>>>(a, B);
+  return cudaGetLastError();
+}
+
 // 8 independent DFMA chains per thread; 16 flop per inner iteration per thread.
 __global__ void dfma_peak_kernel(double* sink, int iters) {
   double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

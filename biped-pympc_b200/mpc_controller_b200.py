@@ -23,8 +23,26 @@ from typing import Tuple
 from . import _native
 
 
-def marshal_inputs(ctrl, fix_layout: bool = False, reproduce_q_stride_bug: bool = False):
-    """The 17 fp64 (B, nnz) tensors of mpc_controller_cusadi.py:77-95 from controller state."""
+def marshal_inputs(ctrl, fix_layout: bool = False, reproduce_q_stride_bug: bool = False, with_linearisation_point=True):
+    """The 17 fp64 (B, nnz) tensors of mpc_controller_cusadi.py:77-95 from controller state, built by ONE
+    kernel (srbd_marshal_inputs) instead of ~25 small torch ops; `marshal_inputs_torch` is the literal
+    torch restatement the tests compare it with.  Only I_world = R I_body R' is still computed by torch
+    (fp32 batched matmul, like the reference: its rounding cannot be reproduced elsewhere)."""
+    import torch
+    sed = ctrl.state_estimate_data
+    rot = sed.rotation_body
+    I_w = rot @ ctrl.biped.I_body.unsqueeze(0) @ rot.transpose(1, 2)
+    f32 = lambda t: torch.as_tensor(t, dtype=torch.float32, device=ctrl.device)
+    return _native.marshal(
+        [f32(ctrl.x0), f32(ctrl.x_ref), f32(ctrl.R_body[:, 0, :, :]), I_w, f32(sed.root_position), f32(sed.foot_position),
+         f32(ctrl.contact_table), f32(ctrl.dt_mpc), f32(ctrl.Q), f32(ctrl.R), f32(ctrl.residual_lin_accel),
+         f32(ctrl.residual_ang_accel)],
+        float(ctrl.mass), float(ctrl.mu), fix_layout, reproduce_q_stride_bug and ctrl.Q.numel() != 12,
+        with_linearisation_point=with_linearisation_point)
+
+
+def marshal_inputs_torch(ctrl, fix_layout: bool = False, reproduce_q_stride_bug: bool = False):
+    """Literal torch restatement of mpc_controller_cusadi.py:54-95 (parity reference of marshal_inputs)."""
     import torch
     B, dev, Hn = ctrl.num_envs, ctrl.device, ctrl.horizon_length
     sed = ctrl.state_estimate_data
@@ -102,7 +120,7 @@ class MPCControllerB200:
             fn = getattr(self, hook, None)
             if fn is not None:
                 fn()
-        inputs = marshal_inputs(self, self.fix_layout, self.reproduce_q_stride_bug)
+        inputs = marshal_inputs(self, self.fix_layout, self.reproduce_q_stride_bug, with_linearisation_point=False)
         foot_wrench = self._ctx.solve(inputs, self.state_estimate_data.rotation_body,
                                       self.MAX_ITER, self.ITERS_PER_CALL, self.tol)
         cost = torch.zeros(self.num_envs, device=self.device)   # reference hard-wires 0 (:185)

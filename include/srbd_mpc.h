@@ -103,6 +103,16 @@ int srbd_pdipm(const double* const* in10, double* const* out6, double* work, int
  * synchronous anyway (generateCUDACode.py:166-177), to pick the fast kernel by itself. */
 int srbd_pdipm_is_stage_invariant(const double* const* in10, int B, void* stream, int* result);
 
+/* Input builder: the marshalling of mpc_controller_cusadi.py:54-95 as one launch.  f32in12 = HOST array
+ * of 12 DEVICE fp32 pointers in this order: x0 (B,12), x_ref (B,10,12), R_body (B,3,3) [= R_body[:,0]],
+ * I_world (B,3,3), root_position (B,3), foot_position (B,2,3), contact_table (B,10,2), dt_mpc (B),
+ * Q (nQ >= 12), R (12), residual_lin_accel (B,3), residual_ang_accel (B,3).  out17: the 17 fp64 (B,nnz)
+ * qp_former inputs; out17[1], out17[2] (x, u) may be NULL.  fix_layout = 0 reproduces the reference's
+ * row-major flattening of R_body / I_world / contact_table into buffers read column-major (SURVEY 8b
+ * Q1, Q2), 1 passes the intended layout; q_stride_bug = 1 reproduces the 13-long Q strided by 12 (Q3). */
+int srbd_marshal_inputs(const float* const* f32in12, int nQ, int fix_layout, int q_stride_bug, double mass, double mu,
+                        double* const* out17, int B, void* stream);
+
 /* u0 = x[120:132] -> body-frame wrench (B,2,6) fp32, mpc_controller_cusadi.py:186-203.
  * rotation_body: device fp32 (B,3,3) row-major. */
 int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, int B, void* stream);

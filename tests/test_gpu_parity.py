@@ -258,6 +258,20 @@ def _fake_controller(B, seed):
     return c, inp, rot
 
 
+@pytest.mark.parametrize("fix_layout,qbug", [(False, False), (True, False), (False, True)])
+def test_input_builder_kernel_equals_torch_marshalling(fix_layout, qbug):
+    """srbd_marshal_inputs (one launch) == the ~25 torch ops of mpc_controller_cusadi.py:54-95, bit for
+    bit, including the layout quirks Q1-Q3 of SURVEY 8b."""
+    c, _, _ = _fake_controller(37, seed=8)
+    a = bp.mpc_controller_b200.marshal_inputs(c, fix_layout, qbug)
+    b = bp.mpc_controller_b200.marshal_inputs_torch(c, fix_layout, qbug)
+    for i, (u, v) in enumerate(zip(a, b)):
+        assert u.dtype == torch.float64 and tuple(u.shape) == (37, bp._native.QP_NNZ_IN[i])
+        assert torch.equal(u, v.reshape(37, -1)), i
+    nox = bp.mpc_controller_b200.marshal_inputs(c, fix_layout, qbug, with_linearisation_point=False)
+    assert nox[1] is None and nox[2] is None and torch.equal(nox[3], a[3])
+
+
 def test_controller_run_matches_oracle_tick():
     B = 6
     c, inp, rot = _fake_controller(B, seed=31)
@@ -265,7 +279,7 @@ def test_controller_run_matches_oracle_tick():
     wrench, cost = c.run()
     assert tuple(wrench.shape) == (B, 2, 6) and wrench.dtype == torch.float32 and tuple(cost.shape) == (B,)
     # oracle: same marshalling (I_world recomputed in fp32 like the reference does)
-    ins = [t.cpu().numpy() for t in bp.mpc_controller_b200.marshal_inputs(c)]
+    ins = [t.cpu().numpy() for t in bp.mpc_controller_b200.marshal_inputs_torch(c)]
     qp = co.qp_former(ins)
     it = co.pdipm(qp, 20, long_double=True)
     from oracle import srbd_oracle as so
