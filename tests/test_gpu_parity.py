@@ -368,6 +368,36 @@ def test_fast_path_rejects_data_that_is_not_qp_former_shaped(golden):
     assert torch.isfinite(gen[0]).all()
 
 
+@pytest.mark.parametrize("B", [1, 13, 14, 15, 29, 2073])
+def test_fused_tick_ragged_batches(B):
+    """CTA boundaries of the fused kernel (14 envs per CTA, 148 CTAs per wave): a batch gives the same
+    per-env answer whatever its size, and the same as assembly + solve + wrench as three launches."""
+    inp, rot = bp.workload.make_batch(B, seed=100 + B)
+    ins = _dev(inp)
+    rot_t = torch.as_tensor(rot, dtype=torch.float32, device=DEV)
+    ctx = bp.Context(B)
+    w, x, s, z, y, res = ctx.solve(ins, rot_t, num_calls=1, iters_per_call=5, want_iterates=True)
+    Hv, f, Av, b, Gv, d = bp.qp_form(ins)
+    out = bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=5, cold_start=True, stage_invariant=True)
+    for g, r in zip((x, s, z, y, res), out[:5]):
+        assert torch.equal(g, r)
+    assert torch.equal(w, bp.wrench(x, rot_t))
+    ctx.close()
+
+
+def test_65536_envs_in_one_launch():
+    """BASELINE configs[2] total size on one GPU: finite, deterministic, independent of the batch position."""
+    B = 65536
+    inp, rot = bp.workload.make_batch(4096, seed=20261018)
+    ins = [t.repeat(16, 1) for t in _dev(inp)]
+    rot_t = torch.as_tensor(rot, dtype=torch.float32, device=DEV).repeat(16, 1, 1)
+    ctx = bp.Context(B)
+    w, x = ctx.solve(ins, rot_t, num_calls=1, iters_per_call=5, want_iterates=True)[:2]
+    assert torch.isfinite(x).all() and torch.isfinite(w).all()
+    assert torch.equal(x[:4096], x[4096 * 15:]) and torch.equal(w[:4096], w[4096 * 7:4096 * 8])
+    ctx.close()
+
+
 def test_full_size_properties():
     """BASELINE config 2 size (4096 envs): size-independent properties instead of the oracle."""
     B = 4096
