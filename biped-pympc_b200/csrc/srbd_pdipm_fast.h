@@ -118,8 +118,6 @@ struct PdipmFast {
   SRBD_DEV double* pr(int hh) const { return sm + SM::OFF_PR + 72 * hh; }
   SRBD_DEV double* psi(int k) const { return sm + SM::OFF_PSI + 14 * k; }
 
-  SRBD_DEV double hsel(double a, double b) const { return h ? b : a; }
-
   // ------------------------------------------------------------------------------------
   // one-time set-up: gather the stage data, derive the iteration-invariant quantities
   // returns nonzero when E or the Mx coefficients are not exactly 1
