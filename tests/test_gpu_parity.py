@@ -70,6 +70,16 @@ def test_qp_form_ragged_batches(B):
     _check_qp(_np(outs), co.qp_former(inp))
 
 
+def test_empty_batches_everywhere():
+    e = lambda n, dt=torch.float64: torch.empty((0, n), dtype=dt, device=DEV)
+    out = bp.pdipm([e(n) for n in bp._native.IP_NNZ_IN[:6]], num_iters=5, cold_start=True, stage_invariant=True)
+    assert [tuple(o.shape) for o in out] == [(0, n) for n in bp._native.IP_NNZ_OUT]
+    ctx = bp.Context(4)
+    w = ctx.solve([e(n) for n in bp._native.QP_NNZ_IN], torch.empty((0, 3, 3), dtype=torch.float32, device=DEV))
+    assert tuple(w.shape) == (0, 2, 6)
+    ctx.close()
+
+
 def test_qp_form_empty_batch():
     empty = [torch.empty((0, n), dtype=torch.float64, device=DEV) for n in bp._native.QP_NNZ_IN]
     out = bp.qp_form(empty)
