@@ -173,8 +173,9 @@ size_t srbd_pdipm_work_doubles(int B) { return B > 0 ? (size_t)B * PDIPM_WORK_DO
 
 int srbd_pdipm(const double* const* in10, double* const* out6, double* work, int* iters_done,
                int B, int num_iters, double tol, unsigned flags, void* stream) {
-  if (!in10 || !out6 || !work || B < 0 || num_iters < 0) return SRBD_EINVAL;
-  if (B == 0) return SRBD_OK;
+  if (!in10 || !out6 || B < 0 || num_iters < 0) return SRBD_EINVAL;
+  if (B == 0) return SRBD_OK;          // empty batch: buffers may legitimately be null
+  if (!work) return SRBD_EINVAL;
   int rc = ensure_init();
   if (rc) return rc;
   PdipmArgs a;
@@ -222,6 +223,7 @@ int srbd_marshal_inputs(const float* const* f32in12, int nQ, int fix_layout, int
 }
 
 int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, int B, void* stream) {
+  if (B == 0) return SRBD_OK;
   if (!x_sol || !rotation_body || !wrench || B < 0) return SRBD_EINVAL;
   SRBD_CUDA(launch_wrench(x_sol, rotation_body, wrench, B, (cudaStream_t)stream));
   return SRBD_OK;
@@ -328,8 +330,8 @@ int srbd_mpc_solve(srbd_ctx* c, const double* const* in17, const float* rotation
                    float* wrench, double* x_out, double* s_out, double* z_out, double* y_out,
                    double* res_out, int* iters_done, void* stream) {
   if (!c || !in17 || B < 0 || B > c->max_B || num_calls < 0 || iters_per_call < 0) return SRBD_EINVAL;
-  if (wrench && !rotation_body) return SRBD_EINVAL;
   if (B == 0) return SRBD_OK;
+  if (wrench && !rotation_body) return SRBD_EINVAL;
   // the reference chains `num_calls` evaluations of a fixed-iteration kernel, feeding
   // (x,s,z,y) back (mpc_controller_cusadi.py:144-169); the iterate sequence is identical to
   // one call with num_calls*iters_per_call iterations, which is what is launched here.
