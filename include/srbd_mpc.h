@@ -130,7 +130,7 @@ int srbd_mpc_solve(srbd_ctx* ctx, const double* const* in17, const float* rotati
                    double* res_out, int* iters_done, void* stream);
 /* EXTENSION (not in the reference, which cold-starts every tick): the same tick warm-started from the
  * previous tick's primal / equality-dual solution.  (x, y) are kept, s = max(h - G x, 1) and z = 1
- * are re-initialised as in the cold start; in the closed-loop rollouts of tools/closed_loop.py 20
+ * are re-initialised as in the cold start; in the closed-loop rollouts of tests/closed_loop.py 20
  * warm iterations per tick do what 30 cold ones do.  x_io / y_io: device buffers holding the previous
  * solution on entry and the new one on return, or both NULL = the context's own buffers (whose first
  * call is then a cold start).  reset: optional device int[B]; envs with reset[e] != 0 (episode

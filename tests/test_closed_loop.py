@@ -1,4 +1,4 @@
-"""Closed-loop rollouts (tools/closed_loop.py): the solve driving a single-rigid-body plant through a
+"""Closed-loop rollouts (tests/closed_loop.py): the solve driving a single-rigid-body plant through a
 walking gait.  Parity of the hot path is unpinned (no CasADi here), so physical sanity of the closed
 loop -- body up, commanded velocity tracked, friction cone respected -- is independent evidence that
 the restated formulation (signs, frames, the Q1 / Q2 layouts of SURVEY 8b) is right.  CPU: the C
@@ -9,14 +9,13 @@ import sys
 import numpy as np
 import pytest
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
 import closed_loop as cl  # noqa: E402
 from oracle import c_oracle as co  # noqa: E402
 
 
 # Newton iterations per tick.  The reference's 4 x 5 cold-started iterations leave |rx| ~ 1..30: on this
 # plant 4 % of random walking envs then bounce more than 8 cm vertically within 3 s, none with 30
-# iterations (tools/closed_loop.py) -- the iteration count is a runtime argument here.
+# iterations (tests/closed_loop.py) -- the iteration count is a runtime argument here.
 ITERS = 30
 
 

@@ -1,7 +1,7 @@
 """Developer tool: run the PDIPM kernel on a few envs on cuda:0 and print the error against the
 long-double C oracle (used with compute-sanitizer / different builds).  Not part of the product."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 import biped_pympc_b200 as bp

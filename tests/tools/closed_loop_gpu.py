@@ -1,7 +1,7 @@
-"""Developer tool: the closed-loop rollout of tools/closed_loop.py on the CUDA path, cold- and warm-started."""
+"""Developer tool: the closed-loop rollout of tests/closed_loop.py on the CUDA path, cold- and warm-started."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 import closed_loop as cl, biped_pympc_b200 as bp
 

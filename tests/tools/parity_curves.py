@@ -2,7 +2,7 @@
 relative error of x, s, z, y against the 80-bit C oracle, for the double C oracle (the reference
 formulation evaluated in fp64) and for the kernel code run under the CPU warp emulator."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import biped_pympc_b200 as bp
