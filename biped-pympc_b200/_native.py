@@ -18,7 +18,7 @@ QP_NNZ_IN = (12, 120, 120, 120, 1, 1, 1, 9, 9, 3, 3, 3, 20, 12, 12, 3, 3)
 QP_NNZ_OUT = (240, 240, 1196, 140, 280, 160)
 IP_NNZ_IN = (240, 280, 1196, 240, 160, 140, 240, 160, 160, 140)
 IP_NNZ_OUT = (240, 160, 160, 140, 4, 1)
-WORK_DOUBLES = 1344
+WORK_DOUBLES = 6224
 
 _lib = None
 _P = ctypes.POINTER(ctypes.c_double)

@@ -31,6 +31,7 @@ struct PdipmArgs {
   const float* rot;             // optional (B,3,3) fp32 row-major state-estimate rotation
   float* wrench;                // optional (B,2,6) fp32 (mpc_controller_cusadi.py:186-203)
 };
-constexpr int PDIPM_WORK_DOUBLES = 1344;  // dx,dy,ds,dz (affine) + D, 1/W, D*g, r2 per inequality row
+constexpr int PDIPM_WORK_DOUBLES = 6224;  // per env: directions + per-row barrier data (1 344) and, for the general
+                                          // kernel, the ten stage buffers prepared once per call (10 x 488)
 
 }  // namespace srbd

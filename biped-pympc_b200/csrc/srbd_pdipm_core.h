@@ -61,8 +61,10 @@ enum : int { ST_ZERO = 0, ST_AU, ST_E, ST_AXPREV, ST_AXCUR, ST_G, ST_Q, ST_QINV,
 struct StageSlot { unsigned char kind; short rel; };
 
 // per-env scratch in global memory (L2 resident): affine direction + per-row barrier data
-enum : int { WK_DX = 0, WK_DY = 240, WK_DS = 380, WK_DZ = 540, WK_D = 700, WK_WI = 860, WK_DG = 1020, WK_R2 = 1180 };
-static_assert(WK_R2 + 160 <= PDIPM_WORK_DOUBLES, "work buffer too small");
+enum : int { WK_DX = 0, WK_DY = 240, WK_DS = 380, WK_DZ = 540, WK_D = 700, WK_WI = 860, WK_DG = 1020, WK_R2 = 1180,
+             WK_STAGE = 1344, WK_STAGE_STRIDE = 488 };   // general kernel: the ten stage buffers, prepared once
+static_assert(WK_STAGE + 10 * WK_STAGE_STRIDE <= PDIPM_WORK_DOUBLES, "work buffer too small");
+static_assert(WK_R2 + 160 <= WK_STAGE, "work buffer layout");
 
 template <bool kUniform>
 struct PdipmSmem {
@@ -134,25 +136,27 @@ struct PdipmWarp {
   // ------------------------------------------------------------------------------------
   // stage data: gather from the CCS value vectors + derived (iteration-invariant) quantities
   // ------------------------------------------------------------------------------------
+  // value of raw slot i of stage k, gathered from the CCS value vectors
+  SRBD_DEV double gather_slot(int i, int k) const {
+    const StageSlot sl = slots[i];
+    double v = 0.0;
+    switch (sl.kind) {
+      case ST_AU: v = ldg(gA + 336 + 86 * k + sl.rel); break;
+      case ST_E: v = ldg(gA + a_xcol_start(k, sl.rel)); break;
+      case ST_AXPREV: if (k >= 1) v = ldg(gA + 36 * (k - 1) + sl.rel); break;
+      case ST_AXCUR: if (k <= 8) v = ldg(gA + 36 * k + sl.rel); break;
+      case ST_G: v = ldg(gG + 28 * k + sl.rel); break;
+      case ST_Q: v = ldg(gQ + 12 * k + sl.rel); break;
+      case ST_QINV: v = rcp(ldg(gQ + 12 * k + sl.rel) + IP_BETA); break;
+      case ST_QINVPREV: if (k >= 1) v = rcp(ldg(gQ + 12 * (k - 1) + sl.rel) + IP_BETA); break;
+      case ST_EPREV: if (k >= 1) v = ldg(gA + a_xcol_start(k - 1, sl.rel)); break;
+      default: break;
+    }
+    return v;
+  }
   SRBD_DEV void load_stage_raw(int hh, int k, int first, int step) const {
     double* s = sb(hh);
-    for (int i = first; i < SB_RAW_END; i += step) {
-      const StageSlot sl = slots[i];
-      double v = 0.0;
-      switch (sl.kind) {
-        case ST_AU: v = ldg(gA + 336 + 86 * k + sl.rel); break;
-        case ST_E: v = ldg(gA + a_xcol_start(k, sl.rel)); break;
-        case ST_AXPREV: if (k >= 1) v = ldg(gA + 36 * (k - 1) + sl.rel); break;
-        case ST_AXCUR: if (k <= 8) v = ldg(gA + 36 * k + sl.rel); break;
-        case ST_G: v = ldg(gG + 28 * k + sl.rel); break;
-        case ST_Q: v = ldg(gQ + 12 * k + sl.rel); break;
-        case ST_QINV: v = rcp(ldg(gQ + 12 * k + sl.rel) + IP_BETA); break;
-        case ST_QINVPREV: if (k >= 1) v = rcp(ldg(gQ + 12 * (k - 1) + sl.rel) + IP_BETA); break;
-        case ST_EPREV: if (k >= 1) v = ldg(gA + a_xcol_start(k - 1, sl.rel)); break;
-        default: break;
-      }
-      s[i] = v;
-    }
+    for (int i = first; i < SB_RAW_END; i += step) s[i] = gather_slot(i, k);
   }
   // Abar(j, c) of a compact 24-entry block (0 where structurally absent)
   SRBD_DEV static double abar(const double* A, int j, int c) {
@@ -230,14 +234,54 @@ struct PdipmWarp {
       s[SB_SX0 + q] = dg;
     }
   }
-  // per-round (general) or once (stage-invariant) stage load; all lanes must call
-  SRBD_DEV void stage(int k) {
-    if (!kUniform) {
+  // this lane's coupling rows (registers) from the coefficient slots of stage buffer hh
+  SRBD_DEV void restore_coupling(int hh, int q) {
+    const double* c0 = sb(hh) + SB_CM; const double* c1 = c0 + 36;
+    const int qq = q < 12 ? q : 0;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { cidx[t][a] = qq; cval[t][a] = 0.0; }
+    if (q < 12) {
+      cval[0][0] = c0[q]; cval[1][0] = c1[q];
+      if (q < 3) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { cidx[0][1 + j] = 6 + j; cval[0][1 + j] = c0[12 + 3 * q + j]; }
+      } else if (q < 6) { cidx[0][1] = q + 6; cval[0][1] = c0[21 + q - 3]; }
+      else if (q < 9) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { cidx[1][1 + i] = i; cval[1][1 + i] = c1[24 + 3 * (q - 6) + i]; }
+      } else { cidx[1][1] = q - 6; cval[1][1] = c1[33 + q - 9]; }
+    }
+  }
+  // general kernel: the ten stages do not fit in shared memory.  Their stage buffers (gathered values +
+  // everything derived from them) are prepared ONCE per call and parked in the work buffer; the
+  // per-round reload is then a coalesced 488-double copy instead of 318 scattered, switch-dispatched
+  // loads plus the derivation
+  SRBD_DEV void prepare_stages() {
+#pragma unroll 1
+    for (int t = 0; t < 5; ++t) {
+      const int k = 2 * t + h;
       w.sync();
       load_stage_raw(h, k, r, 16);
       w.sync();
       stage_derived(h, r);
       w.sync();
+      const double* s = sb(h);
+      double* dst = ws + WK_STAGE + WK_STAGE_STRIDE * k;
+      for (int i = r; i < SB_SIZE; i += 16) dst[i] = s[i];
+    }
+    w.sync();
+  }
+  // per-round (general) or once (stage-invariant) stage load; all lanes must call
+  SRBD_DEV void stage(int k, int lo = 0, int hi = SB_SIZE) {
+    if (!kUniform) {
+      w.sync();
+      double* s = sb(h);
+      const double* src = ws + WK_STAGE + WK_STAGE_STRIDE * k;
+      for (int i = lo + r; i < hi; i += 16) s[i] = src[i];
+      w.sync();
+      restore_coupling(h, r);
     }
   }
   SRBD_DEV void stage_once() {
@@ -470,7 +514,7 @@ struct PdipmWarp {
       if (t < 4) { k = h ? 9 - t : t; nb = h ? k + 1 : k - 1; type = h; }
       else if (t == 4) { k = h ? 5 : 4; nb = h ? 6 : 3; type = h; }
       else { k = 5; nb = 4; type = 0; act = (h == 0); }
-      stage(k);
+      stage(k, SB_CM, SB_CM + 72);   // the substitution rounds only use the coupling rows
       double tv[12];
       ld12(vy + 12 * nb, tv);
       const double q = prow_dot(P(nb), tv);
@@ -492,7 +536,7 @@ struct PdipmWarp {
       if (k > 9) k = 9;
       const int nb = (t == 0) ? -1 : (h ? k - 1 : k + 1);
       const int type = h ? 0 : 1;
-      stage(k);
+      stage(k, SB_CM, SB_CM + 72);
       double tk = vy[12 * k + rr];
       if (nb >= 0) {
 #pragma unroll
@@ -625,6 +669,7 @@ struct PdipmWarp {
       for (int i = lane; i < NINEQ; i += 32) { oS[i] = is[i]; oZ[i] = iz[i]; }
       for (int i = lane; i < NEQ; i += 32) oY[i] = iy[i];
     }
+    if (!kUniform) prepare_stages();
     w.sync();
     stage_once();
 

@@ -5,6 +5,7 @@ import subprocess
 
 import numpy as np
 
+import biped_pympc_b200 as bp
 from oracle import srbd_oracle as so
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
@@ -84,7 +85,7 @@ def emul_pdipm(qp, iters, x=None, s=None, z=None, y=None, tol=0.0, uniform=True,
            zeros(160) if cold else z, zeros(140) if cold else y]
     ins = [np.ascontiguousarray(a, dtype=np.float64) for a in ins]
     outs = [np.zeros((B, n)) for n in (240, 160, 160, 140, 4, 1)]
-    work = np.zeros((B, 1344))   # = PDIPM_WORK_DOUBLES (srbd_args.h)
+    work = np.zeros((B, bp._native.WORK_DOUBLES))   # = PDIPM_WORK_DOUBLES (srbd_args.h)
     itd = np.zeros(B, np.int32)
     P = ctypes.POINTER(ctypes.c_double)
     inarr = (P * 10)(*[a.ctypes.data_as(P) for a in ins])
@@ -106,7 +107,7 @@ def emul_tick(inputs17, rot, iters, tol=0.0, lane_order=1, pair=False, warm_from
     if warm_from is not None:                 # (x, y) of the previous tick, found in the output buffers
         outs[0][:] = warm_from[0]; outs[3][:] = warm_from[1]
     rst = None if reset is None else np.ascontiguousarray(reset, dtype=np.int32)
-    work = np.zeros((B, 1344))
+    work = np.zeros((B, bp._native.WORK_DOUBLES))
     wrench = np.zeros((B, 2, 6), np.float32)
     itd = np.zeros(B, np.int32)
     P = ctypes.POINTER(ctypes.c_double)
