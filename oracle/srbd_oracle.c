@@ -3,10 +3,13 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may build, load or call this file.  The product (biped-pympc_b200/) never does.
  *
- * PARITY UNPINNED: CasADi is not available offline and the reference ships no golden
- * vectors for this path (see oracle/srbd_oracle.py for the full statement).  This is a C
- * restatement of the same two reference functions, checked against the numpy restatement
- * and the committed fixtures by tests/test_oracle_c.py:
+ * PARITY PINNED TO THE REFERENCE'S SOURCE, NOT TO CASADI: CasADi is not available offline and the
+ * reference ships no golden vectors for this path.  The committed fixture
+ * tests/golden/srbd_ref_shim_v1.npz is what the reference's own unmodified Python files compute when
+ * executed over a numeric stand-in for the casadi module (tests/golden/make_golden_ref.py; full
+ * statement in oracle/srbd_oracle.py); tests/test_reference_pin.py checks this file against it
+ * (assembly <= 1e-12, iterates <= 1e-9 after the reference's 5 iterations), tests/test_oracle_c.py
+ * against the numpy restatement.  This is a C restatement of the same two reference functions:
  *
  *   srbd_oracle_qp_former  <- biped_pympc/casadi/srbd_constraints.py:20-227 with the dynamics
  *                             of biped_pympc/casadi/srbd_centroidal_model.py:101-166 (literal

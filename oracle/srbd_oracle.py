@@ -4,12 +4,26 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 ``--impl reference`` legs may import this module.  The product path
 (``biped-pympc_b200``) never imports anything under ``oracle/``.
 
-PARITY UNPINNED.  The reference defines this path as two CasADi ``SX`` functions
-(``qp_former`` and ``sparse_pdipm_multiple_iterations``).  CasADi (unpinned in the
-reference's ``pyproject.toml:17``; CusADi was built against 3.6.5) is not installed
-in this image and cannot be installed (no network); the reference ships no test,
-golden vector or serialized function for the path (``test/`` is empty).  This file
-is therefore a *restatement* of the published algorithm, written by reading
+PARITY PINNED TO THE REFERENCE'S SOURCE, NOT TO CASADI.  The reference defines this path as
+two CasADi ``SX`` functions (``qp_former`` and ``sparse_pdipm_multiple_iterations``).
+CasADi (unpinned in the reference's ``pyproject.toml:17``; CusADi was built against
+3.6.5) is not installed in this image and cannot be installed (no network); the
+reference ships no test, golden vector or serialized function for the path (``test/``
+is empty).  What pins this file: ``tests/golden/make_golden_ref.py`` imports the
+reference's unmodified ``srbd_centroidal_model.py`` / ``srbd_constraints.py`` /
+``sparse_pdipm_solver.py`` from ``/root/reference`` and executes them over a numeric
+stand-in for the ``casadi`` module (``tests/golden/casadi_shim/casadi.py``); the
+committed fixture ``tests/golden/srbd_ref_shim_v1.npz`` holds the patterns and outputs
+that code produces, and ``tests/test_reference_pin.py`` checks this restatement against
+it (patterns identical, assembly <= 1e-12, iterates <= 1e-9 after the reference's 5
+iterations).  What stays unpinned is CasADi's own floating-point operation order
+(AMD ordering inside ``ca.ldl``, QR inside ``ca.inv``): the stand-in restates those
+calls' published semantics, not their code, so agreement with real CasADi is expected
+at the round-off level the reference itself quotes for GPU-vs-CPU ("~1e-10 or
+smaller", ``biped_pympc/cusadi/README.md:126``).  ``tests/test_reference_pin.py`` re-runs the
+generator over real CasADi whenever ``import casadi`` succeeds (it never does here).
+
+This file is a *restatement* of the published algorithm, written by reading
 
   biped_pympc/casadi/srbd_centroidal_model.py:101-166   (dynamics, RK4)
   biped_pympc/casadi/srbd_constraints.py:20-227         (qp_former: H,f,A,b,G,d)
@@ -20,12 +34,7 @@ is therefore a *restatement* of the published algorithm, written by reading
 
 It keeps the reference's variable order, CCS (column-major) nonzero order,
 constants and operation *semantics* (full 700x700 regularised KKT, LDL^T without
-pivoting, two solves sharing one factorisation, ratio tests, clamps).  What it
-cannot reproduce is CasADi's floating-point operation order (AMD ordering inside
-``ca.ldl``, QR inside ``ca.inv``); agreement with real CasADi is expected at the
-round-off level the reference itself quotes for GPU-vs-CPU ("~1e-10 or smaller",
-``biped_pympc/cusadi/README.md:126``).  ``tests/test_casadi_optional.py`` checks this
-file against real CasADi whenever ``import casadi`` succeeds.
+pivoting, two solves sharing one factorisation, ratio tests, clamps).
 
 Everything here is per environment, float64 (or ``np.longdouble`` where noted).
 """

@@ -446,3 +446,70 @@ def test_full_size_properties():
     # the general (stage-varying) path gives the same answer to round-off
     gen = bp.pdipm([t[:256].contiguous() for t in (Hv, Gv, Av, f, d, b)], num_iters=5, cold_start=True, stage_invariant=False)
     assert rel_err(gen[0].cpu().numpy(), out5[0][:256].cpu().numpy()) < 1e-9
+
+
+# ---- against the reference's own source executed over the CasADi stand-in ----------------------
+# (tests/golden/srbd_ref_shim_v1.npz, generator tests/golden/make_golden_ref.py; see
+#  tests/test_reference_pin.py for what the fixture is and for the CPU side of the same checks)
+@pytest.fixture(scope="module")
+def ref():
+    import os
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "srbd_ref_shim_v1.npz")))
+
+
+def _worst_vs_ref(out, ref, it):
+    return {n: max(rel_err(out[i][e], ref[f"ip{it}_{n}"][e]) for e in range(out[i].shape[0]))
+            for i, n in enumerate("xszy")}
+
+
+def test_qp_form_matches_the_reference_code(ref):
+    got = _np(bp.qp_form(_dev([ref[f"in_{n}"] for n in bp.workload.INPUT_NAMES])))
+    _check_qp(got, [ref[f"qp_{n}"] for n in "HfAbGd"])
+
+
+@pytest.mark.parametrize("stage_invariant", [True, False])
+def test_pdipm_matches_the_reference_code(ref, stage_invariant):
+    """sparse_pdipm_multiple_iterations(num_iters=5) of the reference (sparse_pdipm_solver.py:357-534)
+    on qp_former's outputs, from the controller's cold start: <= 1e-9 per env and vector."""
+    Hv, f, Av, b, Gv, d = _dev([ref[f"qp_{n}"] for n in "HfAbGd"])
+    out = _np(bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=5, cold_start=True, stage_invariant=stage_invariant))
+    w = _worst_vs_ref(out, ref, 5)
+    assert max(w.values()) < TOL_IP, w
+    assert rel_err(out[4], ref["ip5_res"]) < 1e-8
+    assert rel_err(out[5].reshape(-1), ref["ip5_mu"].reshape(-1)) < 1e-8
+
+
+def test_chained_calls_match_the_reference_code(ref):
+    """The controller's four chained calls (mpc_controller_cusadi.py:144-169).  Beyond the first call
+    the reference itself is only reproducible to the tolerances below on walking contact tables
+    (tests/test_reference_pin.py); the standing problem of srbd_constraints.py:243-288 keeps 1e-9."""
+    Hv, f, Av, b, Gv, d = _dev([ref[f"qp_{n}"] for n in "HfAbGd"])
+    tol = {5: TOL_IP, 10: 1e-8, 15: 5e-7, 20: 5e-6}
+    cur = None
+    for it in (5, 10, 15, 20):
+        ins = [Hv, Gv, Av, f, d, b] + ([] if cur is None else list(cur[:4]))
+        cur = bp.pdipm(ins, num_iters=5, cold_start=cur is None, stage_invariant=True)
+        w = _worst_vs_ref(_np(cur), ref, it)
+        assert max(w.values()) < tol[it], (it, w)
+    out = _np(cur)
+    for i, n in enumerate("xszy"):
+        assert rel_err(out[i][0], ref[f"ip20_{n}"][0]) < TOL_IP
+
+
+def test_fused_tick_matches_the_reference_code(ref):
+    ins = _dev([ref[f"in_{n}"] for n in bp.workload.INPUT_NAMES])
+    B = ins[0].shape[0]
+    rot = torch.eye(3, dtype=torch.float32, device=DEV)[None].repeat(B, 1, 1)
+    ctx = bp.Context(B)
+    w, x, s, z, y, res = ctx.solve(ins, rot, num_calls=1, iters_per_call=5, want_iterates=True)
+    wst = _worst_vs_ref(_np([x, s, z, y]), ref, 5)
+    assert max(wst.values()) < TOL_IP, wst
+    # one launch of 20 iterations == the reference's 4 x 5, at the chained-call tolerance
+    x20 = ctx.solve(ins, rot, num_calls=4, iters_per_call=5, want_iterates=True)[1]
+    assert max(rel_err(x20[e].cpu().numpy(), ref["ip20_x"][e]) for e in range(B)) < 5e-6
+    u0 = ref["ip20_x"][:, 120:132].astype(np.float32)
+    u0[:, 6] = 0; u0[:, 9] = 0                                   # mpc_controller_cusadi.py:193-194
+    want = -u0.reshape(B, 2, 2, 3).transpose(0, 2, 1, 3).reshape(B, 2, 6)   # [foot][f, m]; identity rotation
+    w20 = ctx.solve(ins, rot, num_calls=4, iters_per_call=5)
+    assert np.abs(w20.cpu().numpy() - want).max() <= 1e-3 * max(1.0, np.abs(want).max())
+    ctx.close()
