@@ -27,7 +27,7 @@ _PP = ctypes.POINTER(_P)
 EXPORTED_SYMBOLS = (
     "srbd_version", "srbd_error_string", "srbd_last_cuda_error", "srbd_init",
     "srbd_qp_former_nnz_in", "srbd_qp_former_nnz_out", "srbd_pdipm_nnz_in", "srbd_pdipm_nnz_out",
-    "srbd_pattern", "srbd_marshal_inputs", "srbd_qp_form", "srbd_pdipm_work_doubles", "srbd_pdipm", "srbd_pdipm_is_stage_invariant", "srbd_wrench",
+    "srbd_pattern", "srbd_reference_trajectory", "srbd_marshal_inputs", "srbd_qp_form", "srbd_pdipm_work_doubles", "srbd_pdipm", "srbd_pdipm_is_stage_invariant", "srbd_wrench",
     "srbd_ctx_create", "srbd_ctx_destroy", "srbd_mpc_solve", "srbd_mpc_solve_warm", "srbd_mpc_solve_host",
     "srbd_qp_former_evaluate", "srbd_sparse_pdipm_multiple_iterations_evaluate", "srbd_dfma_peak",
 )
@@ -63,6 +63,7 @@ def load(build_if_missing: bool = True):
     lib.srbd_pdipm_is_stage_invariant.argtypes = [vp, ci, vp, ctypes.POINTER(ci)]
     lib.srbd_marshal_inputs.argtypes = [vp, ci, ci, ci, cd, cd, vp, ci, vp]
     lib.srbd_wrench.argtypes = [vp, vp, vp, ci, vp]
+    lib.srbd_reference_trajectory.argtypes = [vp, cd, vp, vp, vp, vp, vp, ci, vp]
     lib.srbd_ctx_create.argtypes = [ctypes.POINTER(vp), ci, ci]
     lib.srbd_ctx_destroy.argtypes = [vp]
     lib.srbd_mpc_solve.argtypes = [vp, vp, vp, ci, ci, ci, cd, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -167,6 +168,38 @@ def marshal(f32_tensors: Sequence, mass: float, mu: float, fix_layout=False, q_s
         check(lib.srbd_marshal_inputs(_ptr_array(ts), int(ts[8].numel()), int(bool(fix_layout)), int(bool(q_stride_bug)),
                                       float(mass), float(mu), _ptr_array(out, allow_none=True), B, _stream()))
     return out
+
+
+def reference_trajectory(f32_tensors: Sequence, step: float, world_position_desired, yaw_desired, first_run, x0=None, x_ref=None):
+    """base_controller.py:164-257 in one launch: 9 fp32 device tensors (root_euler, root_position,
+    root_angular_velocity_w, root_velocity_w, rotation_body, desired_velocity_b, desired_angular_velocity_b,
+    desired_height, dt_mpc) -> (x0 (B,12), x_ref (B,10,12)) fp32; the knot-point state
+    (world_position_desired, yaw_desired, first_run [torch.bool]) is updated in place."""
+    import torch
+    lib = load()
+    if len(f32_tensors) != 9:
+        raise ValueError("reference_trajectory: expected 9 tensors")
+    ts = []
+    for i, t in enumerate(f32_tensors):
+        if t.dtype != torch.float32 or t.device.type != "cuda":
+            raise TypeError(f"reference_trajectory: argument {i} must be a float32 CUDA tensor")
+        ts.append(t.contiguous())
+    B, dev = ts[0].shape[0], ts[0].device
+    for name, t, dt, shape in (("world_position_desired", world_position_desired, torch.float32, (B, 3)),
+                               ("yaw_desired", yaw_desired, torch.float32, (B,)), ("first_run", first_run, torch.bool, (B,))):
+        if t.dtype != dt or t.device != dev or tuple(t.shape) != shape or not t.is_contiguous():
+            raise TypeError(f"reference_trajectory: {name} must be a contiguous {dt} tensor of shape {shape} on {dev}")
+    if x0 is None:
+        x0 = torch.empty((B, 12), dtype=torch.float32, device=dev)
+    if x_ref is None:
+        x_ref = torch.empty((B, 10, 12), dtype=torch.float32, device=dev)
+    for name, t, shape in (("x0", x0, (B, 12)), ("x_ref", x_ref, (B, 10, 12))):
+        if t.dtype != torch.float32 or t.device != dev or tuple(t.shape) != shape or not t.is_contiguous():
+            raise TypeError(f"reference_trajectory: {name} must be a contiguous float32 tensor of shape {shape} on {dev}")
+    with torch.cuda.device(dev):
+        check(lib.srbd_reference_trajectory(_ptr_array(ts), float(step), world_position_desired.data_ptr(), yaw_desired.data_ptr(),
+                                            first_run.data_ptr(), x0.data_ptr(), x_ref.data_ptr(), B, _stream()))
+    return x0, x_ref
 
 
 def is_stage_invariant(inputs: Sequence) -> bool:

@@ -222,6 +222,16 @@ int srbd_marshal_inputs(const float* const* f32in12, int nQ, int fix_layout, int
   return SRBD_OK;
 }
 
+int srbd_reference_trajectory(const float* const* f32in9, double step, float* world_position_desired, float* yaw_desired,
+                              unsigned char* first_run, float* x0, float* x_ref, int B, void* stream) {
+  if (B == 0) return SRBD_OK;
+  if (!f32in9 || !world_position_desired || !yaw_desired || !first_run || !x0 || !x_ref || B < 0) return SRBD_EINVAL;
+  for (int i = 0; i < 9; ++i) if (!f32in9[i]) return SRBD_EINVAL;
+  SRBD_CUDA(launch_reference_trajectory(f32in9, (float)step, world_position_desired, yaw_desired, first_run, x0, x_ref, B,
+                                        (cudaStream_t)stream));
+  return SRBD_OK;
+}
+
 int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, int B, void* stream) {
   if (B == 0) return SRBD_OK;
   if (!x_sol || !rotation_body || !wrench || B < 0) return SRBD_EINVAL;

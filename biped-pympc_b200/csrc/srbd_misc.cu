@@ -120,6 +120,71 @@ cudaError_t launch_marshal(const float* const* f32in12, int nQ, int fix_layout, 
   return cudaGetLastError();
 }
 
+// State builder: compute_knot_points + set_initial_state + compute_reference_trajectory of
+// biped_pympc/convex_mpc/base_controller.py:164-257 (about 40 small fp32 torch kernels per tick in the
+// reference) as one launch.  One warp per env: lane 0 updates the open-loop knot point
+// (world_position_desired, yaw_desired, first_run) and writes x0, lanes 0..9 write one stage of x_ref each.
+// Arithmetic is fp32 with the reference's operation order and NO fused multiply-add (__fmul_rn /
+// __fadd_rn), so every entry equals what the torch expressions give, except the body->world velocity
+// (a 3x3 torch.bmm there, whose accumulation order is the BLAS back-end's): (R0 v0 + R1 v1) + R2 v2 here.
+struct RefTrajArgs {
+  const float *euler, *pos, *omega_w, *vel_w, *rot, *v_des_b, *w_des_b, *height, *dt_mpc;
+  float step;                       // cfg.decimation * cfg.dt, rounded to fp32 like torch's scalar
+  float *wpd, *yaw_des;             // (B,3), (B): in / out
+  unsigned char* first_run;         // (B) torch.bool: in / out
+  float *x0, *x_ref;                // (B,12), (B,10,12)
+};
+__global__ void reference_trajectory_kernel(RefTrajArgs a, int B) {
+  const long long e = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (e >= B) return;
+  const float px = a.pos[e * 3], py = a.pos[e * 3 + 1];
+  const float vbx = a.v_des_b[e * 3], vby = a.v_des_b[e * 3 + 1], vbz = a.v_des_b[e * 3 + 2];
+  const float wz = a.w_des_b[e * 3 + 2], h = a.height[e];
+  // knot point (base_controller.py:164-176, 221-225); every lane computes it, lane 0 stores it
+  float wx_d = a.wpd[e * 3], wy_d = a.wpd[e * 3 + 1], yaw_d = a.yaw_des[e];
+  if (a.first_run[e]) { wx_d = px; wy_d = py; yaw_d = a.euler[e * 3 + 2]; }
+  wx_d = __fadd_rn(wx_d, __fmul_rn(a.step, vbx));
+  wy_d = __fadd_rn(wy_d, __fmul_rn(a.step, vby));
+  yaw_d = __fadd_rn(yaw_d, __fmul_rn(a.step, wz));
+  __syncwarp();                                   // all lanes have read the in / out buffers
+  // desired velocity in the world frame (base_controller.py:239)
+  const float* R = a.rot + e * 9;
+  const float vwx = __fadd_rn(__fadd_rn(__fmul_rn(R[0], vbx), __fmul_rn(R[1], vby)), __fmul_rn(R[2], vbz));
+  const float vwy = __fadd_rn(__fadd_rn(__fmul_rn(R[3], vbx), __fmul_rn(R[4], vby)), __fmul_rn(R[5], vbz));
+  const bool stationary = fabsf(vbx) < 1e-2f;     // :227
+  if (lane < N) {
+    const float tb = __fmul_rn(a.dt_mpc[e], (float)lane);                      // :218
+    float4* o = reinterpret_cast<float4*>(a.x_ref + (e * N + lane) * 12);
+    const float yaw = __fadd_rn(yaw_d, __fmul_rn(wz, tb));                     // :234 (:237-238 is the same expression)
+    const float x = __fadd_rn(stationary ? wx_d : px, __fmul_rn(vwx, tb));     // :240, :245
+    const float y = __fadd_rn(stationary ? wy_d : py, __fmul_rn(vwy, tb));     // :241, :246
+    o[0] = make_float4(0.f, 0.f, yaw, x);
+    o[1] = make_float4(y, h, 0.f, 0.f);
+    o[2] = make_float4(wz, vwx, vwy, 0.f);
+  }
+  if (lane < 12) {                                 // set_initial_state, :204-211
+    const float* src = lane < 3 ? a.euler : lane < 6 ? a.pos : lane < 9 ? a.omega_w : a.vel_w;
+    a.x0[e * 12 + lane] = src[e * 3 + lane % 3];
+  }
+  if (lane == 0) {
+    a.wpd[e * 3] = wx_d; a.wpd[e * 3 + 1] = wy_d; a.wpd[e * 3 + 2] = h;     // :224
+    a.yaw_des[e] = yaw_d;
+    a.first_run[e] = 0;
+  }
+}
+
+cudaError_t launch_reference_trajectory(const float* const* f32in9, float step, float* wpd, float* yaw_des,
+                                        unsigned char* first_run, float* x0, float* x_ref, int B, cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  RefTrajArgs a;
+  a.euler = f32in9[0]; a.pos = f32in9[1]; a.omega_w = f32in9[2]; a.vel_w = f32in9[3]; a.rot = f32in9[4];
+  a.v_des_b = f32in9[5]; a.w_des_b = f32in9[6]; a.height = f32in9[7]; a.dt_mpc = f32in9[8];
+  a.step = step; a.wpd = wpd; a.yaw_des = yaw_des; a.first_run = first_run; a.x0 = x0; a.x_ref = x_ref;
+  reference_trajectory_kernel<<<(B + 3) / 4, 128, 0, stream>>>(a, B);
+  return cudaGetLastError();
+}
+
 // 8 independent DFMA chains per thread; 16 flop per inner iteration per thread.
 __global__ void dfma_peak_kernel(double* sink, int iters) {
   double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

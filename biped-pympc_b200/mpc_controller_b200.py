@@ -3,9 +3,10 @@
 
 ``MPCControllerB200.run()`` takes and returns exactly what the reference's ``run()`` does
 (``foot_wrench (B,2,6) fp32, cost (B,)``) and consumes the same controller attributes
-(``x0, x_ref, R_body, contact_table, dt_mpc, mass, mu, Q, R, residual_*_accel`` and
-``state_estimate_data.{rotation_body, root_position, foot_position}`` prepared by
-``BaseMPCController``, base_controller.py:61-257), so ``BipedController`` only needs a new
+(``contact_table, dt_mpc, mass, mu, Q, R, residual_*_accel, cfg.{decimation, dt}``,
+``state_estimate_data`` and ``desired_state_data`` as ``BaseMPCController`` holds them,
+base_controller.py:61-257; ``x0 / x_ref / R_body`` are built on the device by ``build_state`` or, with
+``fused_state_builder = False``, by the host class's own methods), so ``BipedController`` only needs a new
 key in its solver switch (biped_controller.py:36-45).  It is written as a mixin-style class
 with no dependency on the reference package (which cannot be imported without CasADi).
 
@@ -114,12 +115,50 @@ class MPCControllerB200:
         self._ctx = _native.Context(self.num_envs, dev_index)
         return self._ctx
 
+    # True: knot points, initial state and reference trajectory come from ONE kernel (build_state) instead of
+    # the host class's ~40 torch ops (base_controller.py:164-257); False: the inherited methods run as they are.
+    fused_state_builder = True
+
+    def build_state(self):
+        """compute_knot_points + compute_horizon_state + set_initial_state + compute_reference_trajectory
+        (base_controller.py:164-257) as one launch of srbd_reference_trajectory.  Needs
+        state_estimate_data, desired_state_data, dt_mpc and cfg.{decimation, dt}; creates the persistent
+        buffers (x0, x_ref, world_position_desired, yaw_desired, first_run) when the host class has not."""
+        import torch
+        sed, des = self.state_estimate_data, self.desired_state_data
+        B, dev = self.num_envs, sed.rotation_body.device
+        def mk(name, shape, dtype=torch.float32, fill=0):
+            t = getattr(self, name, None)
+            if not isinstance(t, torch.Tensor):
+                t = torch.full(shape, fill, dtype=dtype, device=dev)
+                setattr(self, name, t)
+            return t
+
+        wpd = mk("world_position_desired", (B, 3))
+        yaw = mk("yaw_desired", (B,))
+        first = mk("first_run", (B,), torch.bool, True)
+        x0 = mk("x0", (B, 12))
+        x_ref = mk("x_ref", (B, self.horizon_length, 12))
+        f32 = lambda t: torch.as_tensor(t, dtype=torch.float32, device=dev)  # noqa: E731
+        _native.reference_trajectory(
+            [f32(sed.root_euler), f32(sed.root_position), f32(sed.root_angular_velocity_w), f32(sed.root_velocity_w),
+             f32(sed.rotation_body), f32(des.desired_velocity_b), f32(des.desired_angular_velocity_b),
+             f32(des.desired_height), f32(self.dt_mpc)],
+            float(self.cfg.decimation * self.cfg.dt), wpd, yaw, first, x0, x_ref)
+        # compute_horizon_state (:178-196): the current rotation for the whole horizon; the inverse world
+        # inertia and the foot skews it also fills are not read by this back-end
+        self.R_body = sed.rotation_body.unsqueeze(1).expand(-1, self.horizon_length, -1, -1)
+        return x0, x_ref
+
     def run(self) -> Tuple["torch.Tensor", "torch.Tensor"]:
         import torch
-        for hook in ("compute_knot_points", "compute_horizon_state", "set_initial_state", "compute_reference_trajectory"):
-            fn = getattr(self, hook, None)
-            if fn is not None:
-                fn()
+        if self.fused_state_builder and getattr(self, "desired_state_data", None) is not None:
+            self.build_state()
+        else:
+            for hook in ("compute_knot_points", "compute_horizon_state", "set_initial_state", "compute_reference_trajectory"):
+                fn = getattr(self, hook, None)
+                if fn is not None:
+                    fn()
         inputs = marshal_inputs(self, self.fix_layout, self.reproduce_q_stride_bug, with_linearisation_point=False)
         foot_wrench = self._ctx.solve(inputs, self.state_estimate_data.rotation_body,
                                       self.MAX_ITER, self.ITERS_PER_CALL, self.tol)

@@ -113,6 +113,17 @@ int srbd_pdipm_is_stage_invariant(const double* const* in10, int B, void* stream
 int srbd_marshal_inputs(const float* const* f32in12, int nQ, int fix_layout, int q_stride_bug, double mass, double mu,
                         double* const* out17, int B, void* stream);
 
+/* State builder: compute_knot_points + set_initial_state + compute_reference_trajectory of
+ * convex_mpc/base_controller.py:164-257 as one launch (fp32, the reference's operation order, no FMA).
+ * f32in9 = HOST array of 9 DEVICE fp32 pointers: root_euler (B,3), root_position (B,3),
+ * root_angular_velocity_w (B,3), root_velocity_w (B,3), rotation_body (B,3,3 row-major),
+ * desired_velocity_b (B,3), desired_angular_velocity_b (B,3), desired_height (B), dt_mpc (B).
+ * step = cfg.decimation * cfg.dt.  world_position_desired (B,3), yaw_desired (B) and first_run (B bytes,
+ * torch.bool) are the controller's persistent open-loop knot point: read and updated in place
+ * (first_run envs are re-anchored at the current pose, :171-176).  Outputs x0 (B,12), x_ref (B,10,12). */
+int srbd_reference_trajectory(const float* const* f32in9, double step, float* world_position_desired, float* yaw_desired,
+                              unsigned char* first_run, float* x0, float* x_ref, int B, void* stream);
+
 /* u0 = x[120:132] -> body-frame wrench (B,2,6) fp32, mpc_controller_cusadi.py:186-203.
  * rotation_body: device fp32 (B,3,3) row-major. */
 int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, int B, void* stream);

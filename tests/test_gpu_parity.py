@@ -513,3 +513,63 @@ def test_fused_tick_matches_the_reference_code(ref):
     w20 = ctx.solve(ins, rot, num_calls=4, iters_per_call=5)
     assert np.abs(w20.cpu().numpy() - want).max() <= 1e-3 * max(1.0, np.abs(want).max())
     ctx.close()
+
+
+# ---- against the reference's own controller run (tests/golden/srbd_ref_controller_v1.npz) --------
+@pytest.fixture(scope="module")
+def refc():
+    import os
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "srbd_ref_controller_v1.npz")))
+
+
+V_W_COLUMNS = [3, 4, 9, 10]     # entries that go through the body->world velocity (a torch.bmm in the reference)
+
+
+@pytest.mark.parametrize("tick", [0, 1])
+def test_state_builder_kernel_matches_the_reference_controller(refc, tick):
+    """srbd_reference_trajectory (one launch) against x0 / x_ref / knot point as the reference's
+    compute_knot_points + set_initial_state + compute_reference_trajectory left them
+    (base_controller.py:164-257): bit-exact, except the four columns that depend on R @ v_b (the
+    accumulation order of torch.bmm is the BLAS back-end's): 2 fp32 ulp there."""
+    from test_reference_pin import fake_controller_from_fixture
+    t = f"t{tick}_"
+    c = fake_controller_from_fixture(refc, tick, DEV)
+    x0, x_ref = c.build_state()
+    assert np.array_equal(x0.cpu().numpy(), refc[t + "x0"])
+    got, want = x_ref.cpu().numpy(), refc[t + "x_ref"]
+    exact = [k for k in range(12) if k not in V_W_COLUMNS]
+    assert np.array_equal(got[:, :, exact], want[:, :, exact])
+    assert np.abs(got - want).max() <= 2.4e-7 * max(1.0, np.abs(want).max())
+    assert not c.first_run.any()
+    assert np.array_equal(c.yaw_desired.cpu().numpy(), refc[t + "yaw_desired_out"])
+    assert np.array_equal(c.world_position_desired.cpu().numpy(), refc[t + "world_position_desired_out"])
+    assert torch.equal(c.R_body[:, 3], c.state_estimate_data.rotation_body)
+
+
+def test_controller_two_ticks_match_the_reference_controller(refc):
+    """MPCControllerB200.run() -- state builder, input builder, fused tick -- over the two recorded ticks:
+    the 17 marshalled inputs against what the reference handed to qp_former, the wrench against what its
+    run() returned (mpc_controller_cusadi.py:43-205)."""
+    from test_reference_pin import effective_in17, fake_controller_from_fixture
+    c = fake_controller_from_fixture(refc, 0, DEV)
+    c.init_solver()
+    for tick in (0, 1):
+        t = f"t{tick}_"
+        nxt = fake_controller_from_fixture(refc, tick, DEV)       # this tick's estimator state / command
+        for n in ("state_estimate_data", "desired_state_data", "contact_table", "dt_mpc", "residual_lin_accel",
+                  "residual_ang_accel"):
+            setattr(c, n, getattr(nxt, n))
+        wrench, cost = c.run()                                     # knot-point state carries over from tick 0
+        ins = bp.mpc_controller_b200.marshal_inputs(c, reproduce_q_stride_bug=True)
+        want = effective_in17(refc, tick)
+        for i, (n, g, w) in enumerate(zip(bp.workload.INPUT_NAMES, ins, want)):
+            g = g.cpu().numpy()
+            if n in ("x_ref", "I_world"):                          # fp32 matmuls upstream: 2 ulp
+                assert np.abs(g - w).max() <= 2.4e-7 * max(1.0, np.abs(w).max()), n
+            else:
+                assert np.array_equal(g, w), n
+        ref_w = refc[t + "wrench"]
+        assert wrench.dtype == torch.float32 and tuple(wrench.shape) == ref_w.shape
+        assert np.abs(wrench.cpu().numpy() - ref_w).max() <= 1e-3 * max(1.0, np.abs(ref_w).max())
+        assert float(cost.abs().max()) == 0.0
+    c._ctx.close()

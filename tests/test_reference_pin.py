@@ -184,3 +184,89 @@ def test_real_casadi_reproduces_the_fixture_when_available(ref):
     for n in "xszy":
         for e in range(6):
             assert rel_err(got[f"ip5_{n}"][e], ref[f"ip5_{n}"][e]) < (1e-6 if (n == "z" and e == 1) else 5e-9)
+
+
+# ---- the reference's own controller (MPCControllerCusadi.run + BaseMPCController) ----------------
+# tests/golden/srbd_ref_controller_v1.npz, generator tests/golden/make_golden_controller.py: two MPC ticks
+# of 12 envs through the reference's unmodified controller code on the CPU.
+@pytest.fixture(scope="module")
+def refc():
+    return dict(np.load(os.path.join(HERE, "golden", "srbd_ref_controller_v1.npz")))
+
+
+class _Obj:
+    pass
+
+
+def fake_controller_from_fixture(refc, tick, device="cpu", cls=None):
+    """A stand-alone MPCControllerB200 carrying the state the reference controller had at `tick`."""
+    import torch
+    t = f"t{tick}_"
+    f32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device=device)  # noqa: E731
+    c = (cls or bp.MPCControllerB200)()
+    B = refc[t + "x0"].shape[0]
+    c.num_envs, c.device, c.horizon_length = B, torch.device(device), 10
+    sed = _Obj()
+    for n in ("root_euler", "rotation_body", "root_position", "root_angular_velocity_w", "root_velocity_w", "foot_position"):
+        setattr(sed, n, f32(refc[t + n]))
+    des = _Obj()
+    for n in ("desired_velocity_b", "desired_angular_velocity_b", "desired_height"):
+        setattr(des, n, f32(refc[t + n]))
+    c.state_estimate_data, c.desired_state_data = sed, des
+    c.biped = _Obj(); c.biped.I_body = f32(refc["I_body"])
+    c.cfg = _Obj(); c.cfg.dt = float(refc["dt"]); c.cfg.decimation = int(refc["decimation"])
+    c.contact_table = f32(refc[t + "contact_table_in"])
+    c.dt_mpc = f32(refc[t + "dt_mpc"])
+    c.mass, c.mu = float(refc["mass"]), float(refc["mu"])
+    c.Q, c.R = f32(refc["Q"]), f32(refc["R"])
+    c.residual_lin_accel, c.residual_ang_accel = f32(refc[t + "residual_lin_accel"]), f32(refc[t + "residual_ang_accel"])
+    c.world_position_desired = f32(refc[t + "world_position_desired_in"])
+    c.yaw_desired = f32(refc[t + "yaw_desired_in"])
+    c.first_run = torch.as_tensor(refc[t + "first_run_in"], dtype=torch.bool, device=device)
+    c.reproduce_q_stride_bug = True          # the fixture is the reference, quirk Q3 included
+    return c
+
+
+def effective_in17(refc, tick):
+    """The 17 recorded tensors as the generated kernel reads them: (B, nnz) env-major, Q strided by 12."""
+    t = f"t{tick}_"
+    out = []
+    for n, nnz in zip(bp.workload.INPUT_NAMES, bp.workload.INPUT_NNZ):
+        a = refc[t + "in17_" + n]
+        B = a.shape[0]
+        out.append(np.ascontiguousarray(a.reshape(-1)[:B * nnz].reshape(B, nnz)))
+    return out
+
+
+@pytest.mark.parametrize("tick", [0, 1])
+def test_marshalling_restatement_equals_the_reference_controller(refc, tick):
+    """marshal_inputs_torch (the parity reference of the srbd_marshal_inputs kernel) against the tensors the
+    reference's run() handed to qp_former (mpc_controller_cusadi.py:54-95), bit for bit, quirks included."""
+    import torch
+    c = fake_controller_from_fixture(refc, tick)
+    c.x0 = torch.as_tensor(refc[f"t{tick}_x0"]); c.x_ref = torch.as_tensor(refc[f"t{tick}_x_ref"])
+    c.R_body = c.state_estimate_data.rotation_body.unsqueeze(1).repeat(1, 10, 1, 1)
+    got = bp.mpc_controller_b200.marshal_inputs_torch(c, reproduce_q_stride_bug=True)
+    want = effective_in17(refc, tick)
+    assert refc[f"t{tick}_in17_Q"].shape == (12, 13)                       # Q3: 13 weights per env in the buffer
+    assert not np.array_equal(want[13][1], want[13][0])                    # ... so env 1 reads a rotated vector
+    for n, g, w in zip(bp.workload.INPUT_NAMES, got, want):
+        assert np.array_equal(g.numpy().reshape(w.shape), w), n
+
+
+@pytest.mark.parametrize("tick", [0, 1])
+def test_oracle_and_emulated_tick_match_the_reference_controller(refc, tick):
+    """qp_former + cold start + 4 x 5 iterations + wrench post-processing: the restatements and the device
+    code under the emulator against what the reference's run() returned."""
+    t = f"t{tick}_"
+    ins = effective_in17(refc, tick)
+    rot = refc[t + "rotation_body"].astype(np.float64)
+    x20 = co.pdipm(co.qp_former(ins), 20, long_double=True)[0]
+    B = x20.shape[0]
+    assert max(rel_err(x20[e], refc[t + "ip20_x"][e]) for e in range(B)) < 5e-6
+    want = refc[t + "wrench"]
+    outs, wrench = emul_tick(ins, rot, 20)
+    assert max(rel_err(outs[0][e], refc[t + "ip20_x"][e]) for e in range(B)) < 5e-6
+    assert wrench.shape == want.shape == (B, 2, 6)
+    assert np.abs(wrench - want).max() <= 1e-3 * max(1.0, np.abs(want).max())
+    assert np.array_equal(refc[t + "cost"], np.zeros(B, np.float32))
