@@ -232,6 +232,16 @@ int srbd_reference_trajectory(const float* const* f32in9, double step, float* wo
   return SRBD_OK;
 }
 
+int srbd_gait(float* gait_phase, const float* dt_mpc, const int* ssp_durations, const int* dsp_durations, double dt,
+              int advance, int horizon, float* contact_sub_phase, float* swing_sub_phase, int* mpc_table_i32,
+              float* contact_table_f32, int B, void* stream) {
+  if (B == 0) return SRBD_OK;
+  if (!gait_phase || !dt_mpc || !ssp_durations || !dsp_durations || B < 0 || horizon < 0) return SRBD_EINVAL;
+  SRBD_CUDA(launch_gait(gait_phase, dt_mpc, ssp_durations, dsp_durations, (float)dt, advance, horizon, contact_sub_phase,
+                        swing_sub_phase, mpc_table_i32, contact_table_f32, B, (cudaStream_t)stream));
+  return SRBD_OK;
+}
+
 int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, int B, void* stream) {
   if (B == 0) return SRBD_OK;
   if (!x_sol || !rotation_body || !wrench || B < 0) return SRBD_EINVAL;

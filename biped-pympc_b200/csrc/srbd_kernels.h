@@ -27,6 +27,10 @@ cudaError_t launch_marshal(const float* const* f32in12, int nQ, int fix_layout, 
 // estimator state + command (fp32) -> x0, x_ref and the open-loop knot point, base_controller.py:164-257
 cudaError_t launch_reference_trajectory(const float* const* f32in9, float step, float* wpd, float* yaw_des,
                                         unsigned char* first_run, float* x0, float* x_ref, int B, cudaStream_t stream);
+// gait phase -> sub-phases, MPC contact table, phase update (core/gait/gait_generator.py:79-252)
+cudaError_t launch_gait(float* phase, const float* dt_mpc, const int* ssp, const int* dsp, float dt, int advance,
+                        int horizon, float* contact_sub, float* swing_sub, int* table_i32, float* table_f32, int B,
+                        cudaStream_t stream);
 // DFMA micro-benchmark used for the FP64 roofline denominator
 cudaError_t launch_dfma_peak(double* sink, int iters, int blocks, int threads, cudaStream_t stream);
 

@@ -185,6 +185,77 @@ cudaError_t launch_reference_trajectory(const float* const* f32in9, float step, 
   return cudaGetLastError();
 }
 
+// Gait generator: GaitGenerator.get_contact_sub_phase / get_swing_sub_phase / mpc_gait / update_phase of
+// biped_pympc/core/gait/gait_generator.py:79-252 (about 60 small torch kernels per control step, with
+// boolean-mask indexing that synchronises the host) as one launch, one thread per env.  fp32 with the
+// reference's operation order (IEEE division, no FMA): bit-exact.  Outputs are computed from the phase on
+// entry; the phase is advanced afterwards when `advance` is set (the order of BipedController.run_lowlevel,
+// biped_controller.py:120-127).
+struct GaitArgs {
+  float* phase;                  // (B) in / out
+  const float* dt_mpc;           // (B)
+  const int *ssp, *dsp;          // (B,2) single / double support durations in MPC steps [left, right]
+  float dt;
+  int advance, horizon;
+  float *contact_sub, *swing_sub;      // (B,2) or null
+  int* table_i32;                // (B,horizon,2) or null
+  float* table_f32;              // (B,horizon,2) or null
+};
+__global__ void gait_kernel(GaitArgs a, int B) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B) return;
+  const int s0 = a.ssp[2 * e], s1 = a.ssp[2 * e + 1], d0 = a.dsp[2 * e], d1 = a.dsp[2 * e + 1];
+  const int L = (d0 + s0) + (d1 + s1);                                   // gait_cycle_length, :52
+  const float Lf = (float)L, ph = a.phase[e];
+  const float sp0 = __fdiv_rn((float)s0, Lf), sp1 = __fdiv_rn((float)s1, Lf);   // :67-68
+  const float dp0 = __fdiv_rn((float)d0, Lf), dp1 = __fdiv_rn((float)d1, Lf);
+  if (a.contact_sub) {                                                   // :99-137
+    float cl = -1.f, cr = -1.f;
+    const float th1 = __fadd_rn(sp0, dp0), th2 = __fadd_rn(th1, sp1);
+    if (ph < th1) cl = __fdiv_rn(ph, th1);
+    if (ph >= th2) cl = __fdiv_rn(__fsub_rn(ph, th2), dp0);
+    if (!(ph < sp1)) cr = __fdiv_rn(__fsub_rn(ph, sp1), __fadd_rn(__fadd_rn(dp0, sp1), dp1));
+    a.contact_sub[2 * e] = cl; a.contact_sub[2 * e + 1] = cr;
+  }
+  if (a.swing_sub) {                                                     // :139-171
+    float wl = -1.f, wr = -1.f;
+    const float st = __fadd_rn(sp1, dp0), en = __fadd_rn(st, sp0);
+    if (ph >= st && ph < en) wl = __fdiv_rn(__fsub_rn(ph, st), sp0);
+    if (ph < sp1) wr = __fdiv_rn(ph, sp1);
+    a.swing_sub[2 * e] = wl; a.swing_sub[2 * e + 1] = wr;
+  }
+  if (a.table_i32 || a.table_f32) {                                      // :215-252
+    const long long step0 = (long long)(int)__fmul_rn(ph, Lf);           // .int() truncates
+    for (int k = 0; k < a.horizon; ++k) {
+      long long g = (step0 + k) % L;
+      if (g < 0) g += L;                                                 // torch's % follows the divisor's sign
+      const bool p1 = g < s1, p2 = g >= s1 && g < s1 + d0, p3 = g >= s1 + d0 && g < s1 + d0 + s0;
+      const bool rest = !(p1 || p2 || p3);
+      const int cl = (p1 || p2 || rest) ? 1 : 0, cr = (p2 || p3 || rest) ? 1 : 0;
+      const long long o = ((long long)e * a.horizon + k) * 2;
+      if (a.table_i32) { a.table_i32[o] = cl; a.table_i32[o + 1] = cr; }
+      if (a.table_f32) { a.table_f32[o] = (float)cl; a.table_f32[o + 1] = (float)cr; }
+    }
+  }
+  if (a.advance) {                                                       // update_phase, :79-87
+    const float gds = __fmul_rn(Lf, a.dt_mpc[e]);                        // gait_durations_sec, :77
+    float np = __fadd_rn(ph, __fmul_rn(__frcp_rn(gds), a.dt));          // `dt / tensor` is tensor.reciprocal() * dt in torch
+    np = __fsub_rn(np, np > 1.f ? 1.f : 0.f);
+    a.phase[e] = np;
+  }
+}
+
+cudaError_t launch_gait(float* phase, const float* dt_mpc, const int* ssp, const int* dsp, float dt, int advance,
+                        int horizon, float* contact_sub, float* swing_sub, int* table_i32, float* table_f32, int B,
+                        cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  GaitArgs a;
+  a.phase = phase; a.dt_mpc = dt_mpc; a.ssp = ssp; a.dsp = dsp; a.dt = dt; a.advance = advance; a.horizon = horizon;
+  a.contact_sub = contact_sub; a.swing_sub = swing_sub; a.table_i32 = table_i32; a.table_f32 = table_f32;
+  gait_kernel<<<(B + 127) / 128, 128, 0, stream>>>(a, B);
+  return cudaGetLastError();
+}
+
 // 8 independent DFMA chains per thread; 16 flop per inner iteration per thread.
 __global__ void dfma_peak_kernel(double* sink, int iters) {
   double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

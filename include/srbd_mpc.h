@@ -113,6 +113,16 @@ int srbd_pdipm_is_stage_invariant(const double* const* in10, int B, void* stream
 int srbd_marshal_inputs(const float* const* f32in12, int nQ, int fix_layout, int q_stride_bug, double mass, double mu,
                         double* const* out17, int B, void* stream);
 
+/* Gait generator step (core/gait/gait_generator.py:79-252) as one launch: from the gait phase on entry the
+ * contact / swing sub-phases (get_contact_sub_phase :99-137, get_swing_sub_phase :139-171; -1 = not in that
+ * phase) and the MPC contact table (mpc_gait :215-252; int32 as the reference returns it and / or fp32 as
+ * BaseMPCController.set_contact_table stores it), then -- when advance != 0 -- update_phase (:79-87).  Any of the
+ * four outputs may be NULL.  gait_phase (B) fp32 in / out; dt_mpc (B) fp32; ssp / dsp durations (B,2) int32
+ * [left, right] in MPC steps; dt = control time step.  fp32 arithmetic in the reference's order: bit-exact. */
+int srbd_gait(float* gait_phase, const float* dt_mpc, const int* ssp_durations, const int* dsp_durations, double dt,
+              int advance, int horizon, float* contact_sub_phase, float* swing_sub_phase, int* mpc_table_i32,
+              float* contact_table_f32, int B, void* stream);
+
 /* State builder: compute_knot_points + set_initial_state + compute_reference_trajectory of
  * convex_mpc/base_controller.py:164-257 as one launch (fp32, the reference's operation order, no FMA).
  * f32in9 = HOST array of 9 DEVICE fp32 pointers: root_euler (B,3), root_position (B,3),

@@ -573,3 +573,42 @@ def test_controller_two_ticks_match_the_reference_controller(refc):
         assert np.abs(wrench.cpu().numpy() - ref_w).max() <= 1e-3 * max(1.0, np.abs(ref_w).max())
         assert float(cost.abs().max()) == 0.0
     c._ctx.close()
+
+
+# ---- gait generator kernel against a recording of the reference's GaitGenerator -----------------
+def test_gait_kernel_matches_the_reference_gait_generator():
+    """tests/golden/srbd_ref_gait_v1.npz (generator tests/golden/make_golden_gait.py): 32 envs x 400 control
+    steps of the reference class on the CPU, four gaits, sampling time changed mid-run.  Sub-phases, MPC contact
+    table and the phase itself must be bit-identical at every step, through the fused tick() and through the
+    reference-style separate calls."""
+    import os
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "srbd_ref_gait_v1.npz")))
+    B, H, T = g["ssp"].shape[0], int(g["horizon"]), g["table"].shape[0]
+    mk = lambda: bp.GaitGeneratorB200(B, H, float(g["dt"]), torch.as_tensor(g["dt_mpc0"]), torch.as_tensor(g["dsp"]),  # noqa: E731
+                                      torch.as_tensor(g["ssp"]), DEV)
+    fused, sep = mk(), mk()
+    for gen in (fused, sep):
+        gen.gait_phase[:] = torch.as_tensor(g["phase0"], device=DEV)
+    assert np.array_equal(fused.swing_durations_sec.cpu().numpy()[:0], g["swing_durations_sec"][:0])
+    same = lambda a, b: np.array_equal(a, b, equal_nan=True)  # noqa: E731
+    for t in range(T):
+        if t == int(g["switch_step"]):
+            fused.update_sampling_time(torch.as_tensor(g["dt_mpc1"]))
+            sep.update_sampling_time(torch.as_tensor(g["dt_mpc1"]))
+        assert same(fused.gait_phase.cpu().numpy(), g["phase"][t]), t
+        c, s, tab = fused.tick()
+        assert same(c.cpu().numpy(), g["contact_sub"][t]), t
+        assert same(s.cpu().numpy(), g["swing_sub"][t]), t
+        assert np.array_equal(tab.cpu().numpy(), g["table"][t].astype(np.float32)), t
+        if t % 25 == 0:       # the reference's call sequence: three queries, then update_phase
+            sep.gait_phase[:] = torch.as_tensor(g["phase"][t], device=DEV)
+            assert same(sep.get_swing_sub_phase().cpu().numpy(), g["swing_sub"][t])
+            assert same(sep.get_contact_sub_phase().cpu().numpy(), g["contact_sub"][t])
+            assert sep.mpc_gait.dtype == torch.int32 and np.array_equal(sep.mpc_gait.cpu().numpy(), g["table"][t])
+            assert np.array_equal(sep.contact_bool.cpu().numpy(), g["contact_sub"][t] != -1)
+            sep.update_phase()
+            assert same(sep.gait_phase.cpu().numpy(), g["phase"][t + 1])
+    assert same(fused.gait_phase.cpu().numpy(), g["phase"][T])
+    assert same(fused.swing_durations_sec.cpu().numpy(), g["swing_durations_sec"])
+    fused.reset(torch.tensor([0, 3], device=DEV))
+    assert fused.gait_phase[0] == 0 and fused.gait_phase[3] == 0
