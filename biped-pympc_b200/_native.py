@@ -27,7 +27,7 @@ _PP = ctypes.POINTER(_P)
 EXPORTED_SYMBOLS = (
     "srbd_version", "srbd_error_string", "srbd_last_cuda_error", "srbd_init",
     "srbd_qp_former_nnz_in", "srbd_qp_former_nnz_out", "srbd_pdipm_nnz_in", "srbd_pdipm_nnz_out",
-    "srbd_pattern", "srbd_gait", "srbd_reference_trajectory", "srbd_marshal_inputs", "srbd_qp_form", "srbd_pdipm_work_doubles", "srbd_pdipm", "srbd_pdipm_is_stage_invariant", "srbd_wrench",
+    "srbd_pattern", "srbd_loop_buffers_size", "srbd_update_state", "srbd_lowlevel", "srbd_gait", "srbd_reference_trajectory", "srbd_marshal_inputs", "srbd_qp_form", "srbd_pdipm_work_doubles", "srbd_pdipm", "srbd_pdipm_is_stage_invariant", "srbd_wrench",
     "srbd_ctx_create", "srbd_ctx_destroy", "srbd_mpc_solve", "srbd_mpc_solve_warm", "srbd_mpc_solve_host",
     "srbd_qp_former_evaluate", "srbd_sparse_pdipm_multiple_iterations_evaluate", "srbd_dfma_peak",
 )
@@ -63,6 +63,9 @@ def load(build_if_missing: bool = True):
     lib.srbd_pdipm_is_stage_invariant.argtypes = [vp, ci, vp, ctypes.POINTER(ci)]
     lib.srbd_marshal_inputs.argtypes = [vp, ci, ci, ci, cd, cd, vp, ci, vp]
     lib.srbd_wrench.argtypes = [vp, vp, vp, ci, vp]
+    lib.srbd_loop_buffers_size.restype = ctypes.c_size_t
+    lib.srbd_update_state.argtypes = [vp, vp, ci, ci, vp]
+    lib.srbd_lowlevel.argtypes = [vp, vp, vp, vp, cd, ci, ci, ci, vp]
     lib.srbd_gait.argtypes = [vp, vp, vp, vp, cd, ci, ci, vp, vp, vp, vp, ci, vp]
     lib.srbd_reference_trajectory.argtypes = [vp, cd, vp, vp, vp, vp, vp, ci, vp]
     lib.srbd_ctx_create.argtypes = [ctypes.POINTER(vp), ci, ci]

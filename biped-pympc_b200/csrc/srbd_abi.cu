@@ -242,6 +242,51 @@ int srbd_gait(float* gait_phase, const float* dt_mpc, const int* ssp_durations, 
   return SRBD_OK;
 }
 
+namespace {
+bool loop_buffers_ok(const srbd_loop_buffers* b, bool lowlevel) {
+  if (!b) return false;
+  const void* common[] = {b->gait_phase, b->dt_mpc, b->ssp_durations, b->dsp_durations, b->root_position, b->rotation_body,
+                          b->root_velocity_w, b->foot_position, b->q, b->qd, b->p, b->J, b->contact_phase, b->swing_phase,
+                          b->contact_bool};
+  for (const void* p : common) if (!p) return false;
+  if (!lowlevel) {
+    const void* st[] = {b->root_euler, b->root_velocity_b, b->root_angular_velocity_b, b->root_angular_velocity_w, b->v, b->swing_bool};
+    for (const void* p : st) if (!p) return false;
+    return true;
+  }
+  const void* ll[] = {b->swing_time_remaining, b->first_swing, b->p0, b->foot_height, b->cp1, b->cp2, b->desired_velocity_b,
+                      b->feedforward_force, b->foot_placement, b->foot_placement_b, b->pDes, b->vDes, b->tau, b->qDes, b->qdDes,
+                      b->kpjoint, b->kdjoint, b->action};
+  for (const void* p : ll) if (!p) return false;
+  return true;
+}
+}  // namespace
+
+size_t srbd_loop_buffers_size(void) { return sizeof(srbd_loop_buffers); }
+
+int srbd_update_state(const srbd_loop_buffers* buf, const float* state, int state_stride, int B, void* stream) {
+  if (B == 0) return SRBD_OK;
+  if (!loop_buffers_ok(buf, false) || !state || state_stride < 33 || B < 0) return SRBD_EINVAL;
+  UpdateStateArgs a;
+  static_cast<srbd_loop_buffers&>(a) = *buf;
+  a.state = state; a.state_stride = state_stride;
+  SRBD_CUDA(launch_update_state(a, B, (cudaStream_t)stream));
+  return SRBD_OK;
+}
+
+int srbd_lowlevel(const srbd_loop_buffers* buf, const float* kp, const float* kd, const float* torque_limit, double dt,
+                  int world_frame, int advance_gait, int B, void* stream) {
+  if (B == 0) return SRBD_OK;
+  if (!loop_buffers_ok(buf, true) || !kp || !kd || !torque_limit || B < 0) return SRBD_EINVAL;
+  LowLevelArgs a;
+  static_cast<srbd_loop_buffers&>(a) = *buf;
+  for (int i = 0; i < 5; ++i) { a.kp[i] = kp[i]; a.kd[i] = kd[i]; }
+  for (int i = 0; i < 10; ++i) a.torque_limit[i] = torque_limit[i];
+  a.dt = (float)dt; a.world_frame = world_frame; a.advance_gait = advance_gait; a.wrench = buf->feedforward_force;
+  SRBD_CUDA(launch_lowlevel(a, B, (cudaStream_t)stream));
+  return SRBD_OK;
+}
+
 int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, int B, void* stream) {
   if (B == 0) return SRBD_OK;
   if (!x_sol || !rotation_body || !wrench || B < 0) return SRBD_EINVAL;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/srbd_mpc.h"
 #include "srbd_args.h"
 #include "srbd_pattern.h"
 
@@ -31,6 +32,11 @@ cudaError_t launch_reference_trajectory(const float* const* f32in9, float step, 
 cudaError_t launch_gait(float* phase, const float* dt_mpc, const int* ssp, const int* dsp, float dt, int advance,
                         int horizon, float* contact_sub, float* swing_sub, int* table_i32, float* table_f32, int B,
                         cudaStream_t stream);
+// the control step around the MPC tick (srbd_lowlevel.cu); the buffers are the public srbd_loop_buffers
+struct UpdateStateArgs : srbd_loop_buffers { const float* state; int state_stride; };
+struct LowLevelArgs : srbd_loop_buffers { float kp[5], kd[5], torque_limit[10]; float dt; int world_frame, advance_gait; const float* wrench; };
+cudaError_t launch_update_state(const UpdateStateArgs& a, int B, cudaStream_t stream);
+cudaError_t launch_lowlevel(const LowLevelArgs& a, int B, cudaStream_t stream);
 // DFMA micro-benchmark used for the FP64 roofline denominator
 cudaError_t launch_dfma_peak(double* sink, int iters, int blocks, int threads, cudaStream_t stream);
 

@@ -113,6 +113,71 @@ int srbd_pdipm_is_stage_invariant(const double* const* in10, int B, void* stream
 int srbd_marshal_inputs(const float* const* f32in12, int nQ, int fix_layout, int q_stride_bug, double mass, double mu,
                         double* const* out17, int B, void* stream);
 
+/* ---- the control step around the MPC tick (HECTOR biped), SURVEY 8f rank 3 ------------------------ *
+ * Device buffers of one batch of B envs; all fp32 unless noted, shapes in the comments.  The names are     *
+ * the reference's attribute names (core/data/robot_data.py, controllers/*.py).                             */
+typedef struct srbd_loop_buffers {
+  /* gait + swing state, persistent across steps */
+  float* gait_phase;                     /* (B)      GaitGenerator.gait_phase                          in/out */
+  const float* dt_mpc;                   /* (B)                                                              */
+  const int* ssp_durations;              /* (B,2) int32                                                      */
+  const int* dsp_durations;              /* (B,2) int32                                                      */
+  float* swing_time_remaining;           /* (B,2)    SwingLegController.swing_time_remaining           in/out */
+  unsigned char* first_swing;            /* (B,2) torch.bool                                            in/out */
+  float* p0;                             /* (B,2,3)  swing start position                              in/out */
+  const float* foot_height;              /* (B)      set_swing_parameters                                    */
+  const float* cp1;                      /* (B)                                                              */
+  const float* cp2;                      /* (B)                                                              */
+  const float* desired_velocity_b;       /* (B,3)    DesiredStateData.desired_velocity_b                     */
+  /* state estimate: written by srbd_update_state, read by srbd_lowlevel (and by the MPC tick) */
+  float* root_position;                  /* (B,3) */
+  float* root_euler;                     /* (B,3) */
+  float* rotation_body;                  /* (B,3,3) row-major */
+  float* root_velocity_b;                /* (B,3) */
+  float* root_angular_velocity_b;        /* (B,3) */
+  float* root_velocity_w;                /* (B,3) */
+  float* root_angular_velocity_w;        /* (B,3) */
+  float* foot_position;                  /* (B,2,3) world frame */
+  /* leg data: written by srbd_update_state */
+  float* q;                              /* (B,2,5) */
+  float* qd;                             /* (B,2,5) */
+  float* p;                              /* (B,2,3) foot position, body frame */
+  float* v;                              /* (B,2,3) */
+  float* J;                              /* (B,2,6,5) contact Jacobian */
+  float* contact_phase;                  /* (B,2) -1 = swing */
+  float* swing_phase;                    /* (B,2) -1 = stance */
+  float* contact_bool;                   /* (B,2) 0 / 1 as float, like LegControllerData.contact_bool */
+  float* swing_bool;                     /* (B,2) */
+  /* MPC output consumed by srbd_lowlevel */
+  const float* feedforward_force;        /* (B,2,6) = the wrench srbd_mpc_solve returned */
+  /* leg command: written by srbd_lowlevel */
+  float* foot_placement;                 /* (B,2,3) world */
+  float* foot_placement_b;               /* (B,2,3) body */
+  float* pDes;                           /* (B,2,3) */
+  float* vDes;                           /* (B,2,3) */
+  float* tau;                            /* (B,2,5) feed-forward torque J' f of the stance legs */
+  float* qDes;                           /* (B,2,5) */
+  float* qdDes;                          /* (B,2,5) */
+  float* kpjoint;                        /* (B,2,5) */
+  float* kdjoint;                        /* (B,2,5) */
+  float* action;                         /* (B,10)  BipedController.command_joint_torque */
+} srbd_loop_buffers;
+
+/* sizeof(srbd_loop_buffers) of this build, for binding code that mirrors the struct (ctypes.Structure) */
+size_t srbd_loop_buffers_size(void);
+/* MPCController.update_state (mpc_wrapper.py:22-33) as one launch: gait sub-phases + leg_controller.update_gait_data,
+ * LegController.update_data with HECTOR's forward kinematics and contact Jacobian (leg_controller.py:28-70,
+ * core/robot/hector.py:112-232), StateEstimator.set_body_state / update_foot_position (state_estimator.py:22-47).
+ * state: device fp32 (B, state_stride >= 33): [position 3, quaternion wxyz 4, lin vel body 3, ang vel body 3, q 10, qd 10, ...]. */
+int srbd_update_state(const srbd_loop_buffers* buf, const float* state, int state_stride, int B, void* stream);
+/* BipedController.run_lowlevel + command_joint_torque (biped_controller.py:120-127, 144-176) as one launch: swing
+ * time, Raibert foot placement, cubic Bezier swing trajectory (swing_leg_controller.py:146-263,
+ * swing_leg_trajectory.py:97-135), J' f feed-forward torque, analytical IK and PD targets (leg_controller.py:72-119,
+ * hector.py:234-291), the clamped joint torque, and -- when advance_gait != 0 -- GaitGenerator.update_phase.
+ * kp, kd (5), torque_limit (10): HOST arrays.  world_frame: ControllerConf.swing_reference_frame == "world". */
+int srbd_lowlevel(const srbd_loop_buffers* buf, const float* kp, const float* kd, const float* torque_limit, double dt,
+                  int world_frame, int advance_gait, int B, void* stream);
+
 /* Gait generator step (core/gait/gait_generator.py:79-252) as one launch: from the gait phase on entry the
  * contact / swing sub-phases (get_contact_sub_phase :99-137, get_swing_sub_phase :139-171; -1 = not in that
  * phase) and the MPC contact table (mpc_gait :215-252; int32 as the reference returns it and / or fp32 as

@@ -70,6 +70,23 @@ def test_error_paths_do_not_exit():
     assert lib.srbd_mpc_solve_warm(None, None, None, 4, 20, 0.0, None, None, None, None, None, None, None, None, None) == -1
     assert lib.srbd_mpc_solve_host(None, None, None, 4, 4, 5, 0.0, None, None, None) == -1
     assert lib.srbd_wrench(None, None, None, 4, None) == -1
+    assert lib.srbd_reference_trajectory(None, 0.01, None, None, None, None, None, 4, None) == -1
+    assert lib.srbd_gait(None, None, None, None, 0.001, 1, 10, None, None, None, None, 4, None) == -1
+    assert lib.srbd_update_state(None, None, 43, 4, None) == -1
+    assert lib.srbd_lowlevel(None, None, None, None, 0.001, 0, 1, 4, None) == -1
+    empty = bp.biped_controller._LoopBuffers()          # all-null buffers are rejected, not dereferenced
+    assert lib.srbd_update_state(ctypes.byref(empty), None, 43, 4, None) == -1
+
+
+def test_loop_buffers_struct_mirrors_the_header():
+    """ctypes mirror of srbd_loop_buffers: same size and the same field names in the same order."""
+    lib = bp._native.load()
+    assert ctypes.sizeof(bp.biped_controller._LoopBuffers) == lib.srbd_loop_buffers_size()
+    text = open(os.path.join(ROOT, "include", "srbd_mpc.h")).read()
+    body = text[text.index("typedef struct srbd_loop_buffers {"):text.index("} srbd_loop_buffers;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"\*\s*([A-Za-z_0-9]+)\s*;", body)
+    assert names == [n for n, _ in bp.biped_controller._LoopBuffers._fields_]
 
 
 def test_function_specs_mirror_reference_signatures():
