@@ -333,6 +333,20 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_closed_loop(args):
+    """Config 5 (not the default bench line): one JSON line with per-step latency percentiles of the stack."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import closed_loop_stack
+    res = closed_loop_stack.main(B=args.envs, steps=args.steps, decimation=args.decimation, mpc_calls=args.calls if args.calls > 1 else 4,
+                                 iters_per_call=args.iters, warmup=args.warmup)
+    print(json.dumps({"metric": "closed_loop_env_control_steps_per_sec", "value": res["env_control_steps_per_s"], "unit": "env-steps/s",
+                      "n_gpus": 1, "higher_is_better": True, "dtype": "f64 solve / f32 stack", "data": "synthetic",
+                      "config": {"workload": "closed-loop rollout: gait generator + state estimator + HECTOR leg / swing-leg controllers + MPC "
+                                             "(BASELINE configs[4]); SRBD plant with kinematic legs as stand-in simulator, controller calls timed",
+                                 **{k: res[k] for k in ("envs", "control_steps", "decimation", "mpc_iterations_per_tick")}},
+                      **{k: v for k, v in res.items() if k not in ("envs", "control_steps", "decimation", "mpc_iterations_per_tick", "env_control_steps_per_s")}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -345,8 +359,14 @@ def main():
     ap.add_argument("--calls", type=int, default=1, help="chained PDIPM calls per tick")
     ap.add_argument("--iters", type=int, default=ITERS, help="Newton iterations per call")
     ap.add_argument("--tol", type=float, default=0.0, help="> 0: stop an env when rx, rs, re, mu < tol")
+    # BASELINE configs[4]: closed-loop rollout of the whole control stack (tests/closed_loop_stack.py); --steps =
+    # control steps at 1 kHz, --decimation = control steps per MPC tick (10 = the reference's, 1 = MPC every step)
+    ap.add_argument("--closed-loop", action="store_true")
+    ap.add_argument("--decimation", type=int, default=10)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.closed_loop:
+        run_closed_loop(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

@@ -1,5 +1,5 @@
 """Closed-loop rollouts (tests/closed_loop.py): the solve driving a single-rigid-body plant through a
-walking gait.  Parity of the hot path is unpinned (no CasADi here), so physical sanity of the closed
+walking gait.  Besides the fixtures recorded from the reference's own code, physical sanity of the closed
 loop -- body up, commanded velocity tracked, friction cone respected -- is independent evidence that
 the restated formulation (signs, frames, the Q1 / Q2 layouts of SURVEY 8b) is right.  CPU: the C
 oracle on a handful of envs; GPU: the fused CUDA tick on 4 096 envs (BASELINE configs[4] in miniature)."""
@@ -90,3 +90,14 @@ def test_warm_started_ticks_need_fewer_iterations_on_the_gpu():
     ctx.close()
     _check_walk(s)
     assert torch.equal(xw, xc)
+
+
+@pytest.mark.gpu
+def test_whole_stack_closed_loop_stays_upright():
+    """BASELINE configs[4] in small: BipedControllerB200 (gait + estimator + HECTOR leg / swing-leg controllers +
+    MPC every 10th step) driving the SRBD plant with kinematic legs for 0.6 s."""
+    import closed_loop_stack
+    res = closed_loop_stack.main(B=256, steps=600, warmup=5)
+    assert res["upright_fraction"] >= 0.99, res
+    assert res["height_err_max_of_upright"] < 0.1 and res["tilt_cos_min_of_upright"] > 0.9, res
+    assert res["mpc_ticks_timed"] == 60 and res["step_ms_without_mpc"]["p50"] < 1.0
