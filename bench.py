@@ -338,13 +338,13 @@ def run_closed_loop(args):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import closed_loop_stack
     res = closed_loop_stack.main(B=args.envs, steps=args.steps, decimation=args.decimation, mpc_calls=args.calls if args.calls > 1 else 4,
-                                 iters_per_call=args.iters, warmup=args.warmup)
+                                 iters_per_call=args.iters, warmup=args.warmup, graphs=args.graphs)
     print(json.dumps({"metric": "closed_loop_env_control_steps_per_sec", "value": res["env_control_steps_per_s"], "unit": "env-steps/s",
                       "n_gpus": 1, "higher_is_better": True, "dtype": "f64 solve / f32 stack", "data": "synthetic",
                       "config": {"workload": "closed-loop rollout: gait generator + state estimator + HECTOR leg / swing-leg controllers + MPC "
                                              "(BASELINE configs[4]); SRBD plant with kinematic legs as stand-in simulator, controller calls timed",
-                                 **{k: res[k] for k in ("envs", "control_steps", "decimation", "mpc_iterations_per_tick")}},
-                      **{k: v for k, v in res.items() if k not in ("envs", "control_steps", "decimation", "mpc_iterations_per_tick", "env_control_steps_per_s")}}))
+                                 **{k: res[k] for k in ("envs", "control_steps", "decimation", "mpc_iterations_per_tick", "cuda_graphs")}},
+                      **{k: v for k, v in res.items() if k not in ("envs", "control_steps", "decimation", "mpc_iterations_per_tick", "cuda_graphs", "env_control_steps_per_s")}}))
 
 
 def main():
@@ -363,6 +363,7 @@ def main():
     # control steps at 1 kHz, --decimation = control steps per MPC tick (10 = the reference's, 1 = MPC every step)
     ap.add_argument("--closed-loop", action="store_true")
     ap.add_argument("--decimation", type=int, default=10)
+    ap.add_argument("--graphs", type=int, default=1, help="closed loop: replay the control step as a CUDA graph")
     args = ap.parse_args()
     if args.closed_loop:
         run_closed_loop(args)

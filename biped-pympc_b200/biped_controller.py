@@ -175,6 +175,48 @@ class BipedControllerB200:
             _native.check(self._lib.srbd_lowlevel(ctypes.byref(self._buf), self._k["kp"], self._k["kd"], self._k["lim"], self.dt,
                                                   self.world_frame, 1, self.num_envs, self._stream()))
 
+    # ---- CUDA graphs: the launch-bound control step as one graph replay -----------------------------------
+    def capture_graphs(self, state_width: int = 43):
+        """Captures the two step shapes -- update_state + run_lowlevel, and update_state + run_mpc + run_lowlevel --
+        into CUDA graphs over a static (B, state_width) input buffer; `step(state, mpc)` then costs one copy and one
+        graph replay instead of 2 (resp. ~12) launches issued from Python.  The persistent controller state is
+        saved around the warm-up runs capture needs, so capturing does not advance the gait or the knot point."""
+        import torch
+        self._static_state = torch.zeros(self.num_envs, state_width, dtype=torch.float32, device=self.device)
+        m, sw, g = self.mpc_controller, self.swing_leg_controller, self.gait_generator
+
+        knot = ("world_position_desired", "yaw_desired", "first_run")
+        had_knot = all(isinstance(getattr(m, n, None), torch.Tensor) for n in knot)
+        persistent = [g.gait_phase, sw.swing_time_remaining, sw.first_swing, sw.p0] + ([getattr(m, n) for n in knot] if had_knot else [])
+        saved = [t.clone() for t in persistent]
+        self._static_state[:, 3] = 1.0                    # a valid quaternion and leg posture for the warm-up runs
+        self._static_state[:, 2] = 0.55
+        self._static_state[:, 13:23] = torch.tensor([0.0, 0.0, 0.6, -1.2, 0.6] * 2, device=self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.update_state(self._static_state); self.run_mpc(); self.run_lowlevel()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self._graph_low, self._graph_mpc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_low):
+            self.update_state(self._static_state); self.run_lowlevel()
+        with torch.cuda.graph(self._graph_mpc):
+            self.update_state(self._static_state); self.run_mpc(); self.run_lowlevel()
+        for t, v in zip(persistent, saved):
+            t.copy_(v)
+        if not had_knot:
+            m.first_run.fill_(True)                       # the knot point re-anchors at the first real MPC tick
+        return self
+
+    def step(self, state, mpc: bool):
+        """One control step through the captured graphs: update_state -> [run_mpc] -> run_lowlevel; the joint
+        torque is in `self.action` afterwards.  set_command / update_mpc_sampling_time / set_swing_parameters write
+        into the buffers the graphs read, so they keep working between steps."""
+        self._static_state[:, :state.shape[1]].copy_(state)
+        (self._graph_mpc if mpc else self._graph_low).replay()
+        return self.action
+
     def get_action(self):
         return self.action.clone()
 

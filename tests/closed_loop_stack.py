@@ -54,8 +54,9 @@ def hector_ik(p, leg):
 
 
 class StackRollout:
-    def __init__(self, ctrl, seed=0, v_max=0.3):
+    def __init__(self, ctrl, seed=0, v_max=0.3, graphs=False):
         self.c, dev, B = ctrl, ctrl.device, ctrl.num_envs
+        self.graphs = graphs
         g = torch.Generator(device="cpu").manual_seed(seed)
         r = lambda *s: torch.rand(*s, generator=g).to(dev)  # noqa: E731
         yaw = (2 * r(B) - 1) * math.pi
@@ -98,17 +99,20 @@ class StackRollout:
         st[:, 7:10] = torch.einsum("bji,bj->bi", Rm, self.v); st[:, 10:13] = torch.einsum("bji,bj->bi", Rm, self.w)
         st[:, 13:23] = self.q; st[:, 23:33] = self.qd
         # ---- the controller: the timed region -------------------------------------------------------
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timed else None
+        ev = [None, None, None]
+        if timed:
+            ev[0], ev[2] = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         mpc = (k % c.mpc_decimation == 0)
         c.set_command(self.twist, self.height)
         if timed:
             ev[0].record()
-        c.update_state(st)
-        if mpc:
-            c.run_mpc()
-        if timed:
-            ev[1].record()
-        c.run_lowlevel()
+        if self.graphs:
+            c.step(st, mpc)
+        else:
+            c.update_state(st)
+            if mpc:
+                c.run_mpc()
+            c.run_lowlevel()
         if timed:
             ev[2].record()
             self.lat["step"].append((ev[0], ev[2], mpc))
@@ -150,15 +154,17 @@ class StackRollout:
                 "tilt_cos_min_of_upright": float(up[ok].min()) if ok.any() else float("nan")}
 
 
-def main(B=4096, steps=1000, decimation=10, mpc_calls=4, iters_per_call=5, warmup=20, dev="cuda:0", seed=1):
+def main(B=4096, steps=1000, decimation=10, mpc_calls=4, iters_per_call=5, warmup=20, dev="cuda:0", seed=1, graphs=0):
     import biped_pympc_b200 as bp
     c = bp.BipedControllerB200(B, dev, decimation=decimation, mpc_calls=mpc_calls, mpc_iters_per_call=iters_per_call)
-    ro = StackRollout(c, seed=seed)
+    if graphs:
+        c.capture_graphs()
+    ro = StackRollout(c, seed=seed, graphs=bool(graphs))
     lat = ro.run(steps, warmup)
     mpc, low = lat[lat[:, 1] == 1, 0], lat[lat[:, 1] == 0, 0]
     pct = lambda a, p: float(np.percentile(a, p)) if len(a) else None  # noqa: E731
     n_mpc = int((lat[:, 1] == 1).sum())
-    res = {"envs": B, "control_steps": steps, "decimation": decimation, "mpc_iterations_per_tick": mpc_calls * iters_per_call,
+    res = {"envs": B, "cuda_graphs": bool(graphs), "control_steps": steps, "decimation": decimation, "mpc_iterations_per_tick": mpc_calls * iters_per_call,
            "mpc_ticks_timed": n_mpc, "controller_ms_total": float(lat[:, 0].sum()),
            "step_ms_without_mpc": {"p50": pct(low, 50), "p99": pct(low, 99)}, "step_ms_with_mpc": {"p50": pct(mpc, 50), "p99": pct(mpc, 99)},
            "env_control_steps_per_s": float(B * len(lat) / (lat[:, 0].sum() * 1e-3)),

@@ -646,3 +646,33 @@ def test_control_stack_matches_the_reference_stack():
             assert v <= tol.get(n, 2e-6) * scale(n), (n, v, scale(n))
     free = loop_errors.run(g, inject=False, dev=DEV)                # the closed chain, MPC wrench not injected
     assert free["action"] <= 5e-3 * scale("action") and free["first_swing"] == 0.0
+
+
+def test_cuda_graph_step_is_bit_identical_to_the_eager_step():
+    """BipedControllerB200.capture_graphs / step(): the control step replayed as a CUDA graph gives exactly the
+    eager step's joint torques and leaves the same persistent state, over the recorded sensor stream."""
+    import os
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "srbd_ref_loop_v1.npz")))
+    B, dec = g["state"].shape[1], int(g["decimation"])
+    mk = lambda: bp.BipedControllerB200(B, DEV, dt=float(g["dt"]), dt_mpc=float(g["dt_mpc"]), decimation=dec)  # noqa: E731
+    eager, graph = mk(), mk()
+    graph.capture_graphs()
+    for c in (eager, graph):
+        c.gait_generator.gait_phase[:] = torch.as_tensor(g["phase0"], device=DEV)
+    assert bool(graph.swing_leg_controller.first_swing.all()) and float(graph.swing_leg_controller.p0.abs().max()) == 0.0
+    for t in range(60):
+        st = torch.as_tensor(g["state"][t], device=DEV)
+        for c in (eager, graph):
+            c.set_command(torch.as_tensor(g["twist"][t], device=DEV), torch.as_tensor(g["height"][t], device=DEV))
+        eager.update_state(st)
+        if t % dec == 0:
+            eager.run_mpc()
+        eager.run_lowlevel()
+        graph.step(st, t % dec == 0)
+        assert torch.equal(eager.action, graph.action), t
+    for a, b in ((eager.gait_generator.gait_phase, graph.gait_generator.gait_phase),
+                 (eager.swing_leg_controller.first_swing, graph.swing_leg_controller.first_swing),
+                 (eager.mpc_controller.world_position_desired, graph.mpc_controller.world_position_desired),
+                 (eager.leg_controller.command.feedfowardforce, graph.leg_controller.command.feedfowardforce)):
+        assert torch.equal(a, b)
+    eager.close(); graph.close()
