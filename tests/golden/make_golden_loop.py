@@ -6,7 +6,8 @@ unmodified from /root/reference and stepped on the CPU the way its users step it
 
     set_command -> update_state -> [run_mpc every `decimation` steps] -> run_lowlevel -> get_action
 
-with the walking gait (gait_id=2).  As in make_golden_controller.py the only stand-ins are the `casadi`
+with the walking gait (gait_id=2); two short variants cover the `world` swing reference frame and the
+standing gait (gait_id=1).  As in make_golden_controller.py the only stand-ins are the `casadi`
 module and `CusadiFunction` (CPU evaluation of the two rebuilt functions).  The sensor input is an open-loop,
 seeded random walk around a standing posture (this is a recording of the controller's arithmetic, not a
 simulation).  Every intermediate quantity the device-side mirror (biped-pympc_b200/biped_controller.py)
@@ -28,7 +29,7 @@ from make_golden_controller import CpuCusadiFunction  # noqa: E402
 B, STEPS = 6, 160
 
 
-def build_reference_wrapper(num_envs, decimation=10, reference_frame="base"):
+def build_reference_wrapper(num_envs, decimation=10, reference_frame="base", gait_id=2):
     SRBD_Constraints, sparse_pdipm_multiple_iterations = mgr.import_reference()
     import casadi
     wl = mgr.load_workload()
@@ -47,7 +48,7 @@ def build_reference_wrapper(num_envs, decimation=10, reference_frame="base"):
     mpc_cfg = MPCConf(print_solve_time=False, decimation=decimation)
     mpc_cfg.Q, mpc_cfg.R = mpc_cfg.Q.cpu(), mpc_cfg.R.cpu()
     cfg = ControllerConf(swing_reference_frame=reference_frame)
-    return MPCController(cfg, mpc_cfg, num_envs, torch.device("cpu"), gait_id=2), cfg, mpc_cfg
+    return MPCController(cfg, mpc_cfg, num_envs, torch.device("cpu"), gait_id=gait_id), cfg, mpc_cfg
 
 
 def quat_from_euler(r, p, y):
@@ -56,16 +57,17 @@ def quat_from_euler(r, p, y):
                      cr * cp * sy - sr * sp * cy], 1)
 
 
-def main():
-    ctrl, cfg, mpc_cfg = build_reference_wrapper(B)
+def main(B=B, STEPS=STEPS, reference_frame="base", gait_id=2, name="srbd_ref_loop_v1.npz", seed=20261018):
+    ctrl, cfg, mpc_cfg = build_reference_wrapper(B, reference_frame=reference_frame, gait_id=gait_id)
     bc = ctrl.biped_controller
-    rng = np.random.default_rng(20261018)
+    rng = np.random.default_rng(seed)
     bc.gait_generator.gait_phase[:] = torch.as_tensor(rng.uniform(0, 1, B), dtype=torch.float32)
     out = {"phase0": bc.gait_generator.gait_phase.numpy().copy(), "decimation": np.array(mpc_cfg.decimation),
            "dt": np.array(mpc_cfg.dt), "dt_mpc": np.array(mpc_cfg.dt_mpc), "ssp": np.array(cfg.ssp_durations),
            "dsp": np.array(cfg.dsp_durations), "swing_height": np.array(cfg.swing_height),
            "mass": np.array(bc.mpc_controller.mass), "mu": np.array(bc.mpc_controller.mu),
-           "Q": mpc_cfg.Q.numpy(), "R": mpc_cfg.R.numpy()}
+           "Q": mpc_cfg.Q.numpy(), "R": mpc_cfg.R.numpy(), "world_frame": np.array(int(reference_frame == "world")),
+           "gait_id": np.array(gait_id)}
     # open-loop sensor stream: a smooth random walk around a crouched standing posture
     q_nom = np.array([0.0, 0.0, 0.6, -1.2, 0.6] * 2)
     q = q_nom + rng.normal(0, 0.05, (B, 10))
@@ -116,9 +118,11 @@ def main():
     for k, v in rec.items():
         out[k] = np.stack(v)
     out["torque_limit"] = bc.torque_limit.numpy()
-    np.savez_compressed(os.path.join(HERE, "srbd_ref_loop_v1.npz"), **out)
-    print("saved srbd_ref_loop_v1.npz:", {k: v.shape for k, v in out.items() if k in ("state", "action", "leg_J", "wrench")})
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print("saved", name, {k: v.shape for k, v in out.items() if k in ("state", "action", "leg_J", "wrench")})
 
 
 if __name__ == "__main__":
-    main()
+    main()                                                                                  # walking, base frame (defaults)
+    main(B=4, STEPS=70, reference_frame="world", name="srbd_ref_loop_v1_world.npz", seed=7)  # swing targets in the world frame
+    main(B=3, STEPS=30, gait_id=1, name="srbd_ref_loop_v1_standing.npz", seed=9)             # standing gait (swing time 0)

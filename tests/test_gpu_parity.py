@@ -615,7 +615,8 @@ def test_gait_kernel_matches_the_reference_gait_generator():
 
 
 # ---- the whole control step against a recording of the reference stack ------------------------------
-def test_control_stack_matches_the_reference_stack():
+@pytest.mark.parametrize("fixture", ["srbd_ref_loop_v1.npz", "srbd_ref_loop_v1_world.npz", "srbd_ref_loop_v1_standing.npz"])
+def test_control_stack_matches_the_reference_stack(fixture):
     """tests/golden/srbd_ref_loop_v1.npz (generator tests/golden/make_golden_loop.py): 160 control steps x 6 envs
     of the reference's MPCController wrapper (gait generator, state estimator, HECTOR leg controller, swing-leg
     controller, MPC every 10th step) on the CPU.  BipedControllerB200 -- two launches per control step -- must
@@ -627,13 +628,15 @@ def test_control_stack_matches_the_reference_stack():
     x_ref by ONE fp32 ulp moves u0 by up to 0.95 N in the 80-bit oracle -- and x_ref carries a
     torch.bmm upstream (2 ulp between back-ends).  With bit-identical inputs the same solve agrees to 1e-3 /
     3e-5 N (test_controller_two_ticks_match_the_reference_controller, tests/test_reference_pin.py).  Downstream
-    of the MPC the recorded wrench is injected so that the remaining quantities are compared tightly."""
+    of the MPC the recorded wrench is injected so that the remaining quantities are compared tightly.
+    `_world`: swing targets in the world frame (ControllerConf.swing_reference_frame); `_standing`: gait_id = 1,
+    whose zero swing time makes the reference divide by zero (inf / nan in vDes: reproduced position by position)."""
     import os
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path.insert(0, os.path.join(here, "tools"))
     import loop_errors
-    g = dict(np.load(os.path.join(here, "golden", "srbd_ref_loop_v1.npz")))
+    g = dict(np.load(os.path.join(here, "golden", fixture)))
     err = loop_errors.run(g, inject=True, dev=DEV)
     scale = lambda n: max(1.0, float(np.abs(g[n][np.isfinite(g[n])]).max()))  # noqa: E731
     exact = ("leg_contact_bool", "leg_swing_bool", "contact_phase", "swing_phase", "mpc_contact_table", "swing_time_remaining",

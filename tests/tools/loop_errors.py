@@ -14,7 +14,8 @@ import biped_pympc_b200 as bp  # noqa: E402
 def run(g, inject=True, dev="cuda:0"):
     B, T, dec = g["state"].shape[1], g["state"].shape[0], int(g["decimation"])
     c = bp.BipedControllerB200(B, dev, dt=float(g["dt"]), dt_mpc=float(g["dt_mpc"]), decimation=dec, ssp_durations=int(g["ssp"]),
-                               dsp_durations=int(g["dsp"]), swing_height=float(g["swing_height"]), Q=g["Q"], R=g["R"])
+                               dsp_durations=int(g["dsp"]), swing_height=float(g["swing_height"]), Q=g["Q"], R=g["R"],
+                               swing_reference_frame="world" if int(g.get("world_frame", 0)) else "base", gait_id=int(g.get("gait_id", 2)))
     c.mpc_controller.reproduce_q_stride_bug = True
     c.gait_generator.gait_phase[:] = torch.as_tensor(g["phase0"], device=dev)
     err, k = {}, 0
