@@ -227,9 +227,7 @@ class BipedControllerB200:
     def reset(self, env_ids):
         """BipedController.reset (biped_controller.py:83-88)."""
         self.gait_generator.gait_phase[env_ids] = 0.0
-        first = getattr(self.mpc_controller, "first_run", None)
-        if first is not None:
-            first[env_ids] = True
+        self.mpc_controller.reset(env_ids)
         s, ld, c = self.state_estimator.data, self.leg_controller.data, self.leg_controller.command
         for t in (s.root_position, s.root_euler, s.root_velocity_w, s.root_angular_velocity_w, s.foot_position, s.root_velocity_b,
                   s.root_angular_velocity_b, ld.q, ld.qd, ld.J, ld.p, ld.v, ld.contact_phase, ld.swing_phase, c.tau, c.qDes, c.qdDes,

@@ -150,6 +150,13 @@ class MPCControllerB200:
         self.R_body = sed.rotation_body.unsqueeze(1).expand(-1, self.horizon_length, -1, -1)
         return x0, x_ref
 
+    def reset(self, env_ids):
+        """BaseMPCController.reset (base_controller.py:259-266): the knot point of these envs re-anchors at the
+        current pose on the next tick."""
+        first = getattr(self, "first_run", None)
+        if first is not None:
+            first[env_ids] = True
+
     def run(self) -> Tuple["torch.Tensor", "torch.Tensor"]:
         import torch
         if self.fused_state_builder and getattr(self, "desired_state_data", None) is not None:
