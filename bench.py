@@ -143,6 +143,56 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_cusadi_ref(args):
+    """`--impl cusadi`: the reference's CusADi GPU path on this GPU -- the two kernels the reference's own
+    generateCUDACode.py emits (oracle/_ref, built by oracle/make_cusadi_ref.py), called the way CusadiFunction /
+    MPCControllerCusadi call them: outputs and the (B, sz_w) work tensor are zero-filled before each launch
+    (CusadiFunction.py:104-109), one thread per env runs the whole expression tape, synchronous launches.  A step =
+    qp_former + the cold start + ONE sparse_pdipm_multiple_iterations call (5 iterations), like the default arm.
+    Not part of the driver contract; it answers north_star's "next to the reference's CusADi GPU path"."""
+    import torch
+    import biped_pympc_b200 as bp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cusadi_ref
+    missing = [n for n in ("qp_former", "sparse_pdipm_multiple_iterations") if not cusadi_ref.available(n)]
+    if missing:
+        print(json.dumps({"impl": "cusadi", "unavailable": "oracle/_ref/lib%s.so not built (python oracle/make_cusadi_ref.py)" % missing[0]}))
+        return
+    dev, B = "cuda:0", args.envs
+    inp, _ = bp.workload.make_batch(B, seed=20261018)
+    ins = [torch.as_tensor(a, device=dev) for a in inp]
+    former = cusadi_ref.CusadiRefFunction("qp_former", B, dev)
+    solver = cusadi_ref.CusadiRefFunction("sparse_pdipm_multiple_iterations", B, dev)
+    kern = {"qp_former": [], "solver": []}
+
+    def step():
+        kern["qp_former"].append(former.evaluate(ins))
+        Hv, f, Av, b, Gv, d = former.outputs_sparse
+        x = torch.zeros(B, 240, dtype=torch.float64, device=dev)          # mpc_controller_cusadi.py:138-141
+        s = torch.maximum(d, torch.ones_like(d)); z = torch.ones_like(d); y = torch.ones(B, 140, dtype=torch.float64, device=dev)
+        kern["solver"].append(solver.evaluate([Hv, Gv, Av, f, d, b, x, s, z, y]))
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    kern = {"qp_former": [], "solver": []}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    mean = lambda v: 1e3 * sum(v) / len(v)  # noqa: E731
+    print(json.dumps({
+        "impl": "cusadi", "metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{B}-env batched SRBD MPC, 5 PDIPM iters, fp64 (BASELINE configs[1]) through the reference's CusADi-generated "
+                               "kernels (its generateCUDACode.py over its function sources; expression graph from the CasADi stand-in)",
+                   "envs_per_gpu": B, "iters": ITERS},
+        "kernel_ms": {"qp_former": mean(kern["qp_former"]), "sparse_pdipm_multiple_iterations": mean(kern["solver"])},
+        "instructions_per_env": {"qp_former": former.n_instructions, "sparse_pdipm_multiple_iterations": solver.n_instructions},
+        "work_doubles_per_env": {"qp_former": former.sz_w, "sparse_pdipm_multiple_iterations": solver.sz_w}}))
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -352,7 +402,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cusadi"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     # other BASELINE configs (not the default bench line): --calls 4 = the reference tick (4 x 5 iterations,
     # mpc_controller_cusadi.py:144-169); --envs 16384 --iters 30 --tol 1e-8 = run to convergence (config 4)
@@ -369,6 +419,9 @@ def main():
         run_closed_loop(args)
     elif args.impl == "reference":
         run_reference(args)
+    elif args.impl == "cusadi":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_cusadi_ref(args)
     else:
         run_b200(args)
 

@@ -33,6 +33,15 @@ import os
 import numpy as np
 
 # ---------------------------------------------------------------------------------------------
+# instruction op codes (names as in casadi/core/calculus.hpp; the numeric values are the shim's own --
+# callers only ever compare them with these constants, e.g. cusadi/src/CusadiOperations.py:11-111)
+# ---------------------------------------------------------------------------------------------
+(OP_ASSIGN, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_EXP, OP_LOG, OP_POW, OP_CONSTPOW, OP_SQRT, OP_SQ, OP_TWICE, OP_SIN, OP_COS,
+ OP_TAN, OP_ASIN, OP_ACOS, OP_ATAN, OP_LT, OP_LE, OP_EQ, OP_NE, OP_NOT, OP_AND, OP_OR, OP_FLOOR, OP_CEIL, OP_FMOD, OP_FABS, OP_SIGN,
+ OP_COPYSIGN, OP_IF_ELSE_ZERO, OP_ERF, OP_FMIN, OP_FMAX, OP_INV, OP_SINH, OP_COSH, OP_TANH, OP_ASINH, OP_ACOSH, OP_ATANH, OP_ATAN2,
+ OP_CONST, OP_INPUT, OP_OUTPUT, OP_PARAMETER, OP_CALL) = range(49)
+
+# ---------------------------------------------------------------------------------------------
 # scalar expression nodes
 # ---------------------------------------------------------------------------------------------
 _C, _S, _ADD, _SUB, _MUL, _DIV, _NEG, _POW, _LT, _IFE, _FMIN, _FMAX, _SQRT, _NOT = range(14)
@@ -826,6 +835,7 @@ class Function(object):
             for n in m.arr.reshape(-1):
                 assert n is not None and n.op == _S, "Function inputs must be purely symbolic"
         self._tape = None
+        self._instr = None
 
     def name(self):
         return self._name
@@ -865,10 +875,109 @@ class Function(object):
         self._nodes = nodes
         self._order = order
 
-    def n_instructions(self):
+    # -- instruction-level view (SXFunction's algorithm): what code generators walk -------------
+    def _build_instructions(self):
+        """Linearises the tape into CasADi-style instructions over a work vector whose slots are reused once a
+        value is dead (CasADi allocates its work vector the same way; sz_w is the number of simultaneously live
+        values, not the number of instructions).  if_else(c, x, y) is emitted the way CasADi defines it,
+        if_else_zero(c, x) + if_else_zero(!c, y)."""
         if self._tape is None:
             self._build_tape()
-        return len(self._tape)
+        tape, n = self._tape, len(self._tape)
+        sym_pos = {}
+        for i, m in enumerate(self._ins):
+            for e, node in enumerate(m.arr.reshape(-1, order="F")):
+                sym_pos[node.id] = (i, e)
+        out_use = []                                   # (tape position, output index, nonzero index)
+        for o, m in enumerate(self._outs):
+            e = 0
+            r, c = m.arr.shape
+            for j in range(c):
+                for i in range(r):
+                    if m.arr[i, j] is not None:
+                        out_use.append((self._pos[m.arr[i, j].id], o, e))
+                        e += 1
+        last = list(range(n))                          # last instruction position that reads each value
+        for k, (op, a, b, c) in enumerate(tape):
+            if op not in (_C, _S):
+                last[a] = k
+                if op not in (_NEG, _SQRT):
+                    last[b] = k
+                if op == _IFE:
+                    last[c] = k
+        for pos, _, _ in out_use:
+            last[pos] = n                              # outputs are written at the end: keep alive
+        binop = {_ADD: OP_ADD, _SUB: OP_SUB, _MUL: OP_MUL, _DIV: OP_DIV, _POW: OP_POW, _LT: OP_LT, _FMIN: OP_FMIN, _FMAX: OP_FMAX}
+        free, nslot, slot = [], 0, [0] * n
+        ids, ins, outs, consts = [], [], [], []
+        dying = {}
+        for k in range(n):
+            dying.setdefault(last[k], []).append(k)
+
+        def alloc():
+            nonlocal nslot
+            if free:
+                return free.pop()
+            nslot += 1
+            return nslot - 1
+
+        def emit(op, i, o, cval=0.0):
+            ids.append(op); ins.append(i); outs.append(o); consts.append(cval)
+
+        for k, (op, a, b, c) in enumerate(tape):
+            if op == _C:
+                slot[k] = alloc(); emit(OP_CONST, [], [slot[k]], a)
+            elif op == _S:
+                slot[k] = alloc(); emit(OP_INPUT, list(sym_pos[a]), [slot[k]])
+            elif op == _IFE:
+                t1, t2 = alloc(), alloc()
+                emit(OP_IF_ELSE_ZERO, [slot[a], slot[b]], [t1])
+                emit(OP_NOT, [slot[a]], [t2])
+                emit(OP_IF_ELSE_ZERO, [t2, slot[c]], [t2])
+                slot[k] = alloc()
+                emit(OP_ADD, [t1, t2], [slot[k]])
+                free.extend((t1, t2))
+            elif op == _NEG:
+                slot[k] = alloc(); emit(OP_NEG, [slot[a]], [slot[k]])
+            elif op == _SQRT:
+                slot[k] = alloc(); emit(OP_SQRT, [slot[a]], [slot[k]])
+            else:
+                slot[k] = alloc(); emit(binop[op], [slot[a], slot[b]], [slot[k]])
+            for d in dying.get(k, ()):                 # values whose last reader was this instruction
+                if d != k or last[k] == k:
+                    free.append(slot[d])
+        for pos, o, e in out_use:
+            emit(OP_OUTPUT, [slot[pos]], [o, e])
+        self._instr = (ids, ins, outs, consts, nslot)
+
+    def _instructions(self):
+        if getattr(self, "_instr", None) is None:
+            self._build_instructions()
+        return self._instr
+
+    def n_instructions(self):
+        return len(self._instructions()[0])
+
+    def instruction_id(self, k):
+        return self._instructions()[0][k]
+
+    def instruction_input(self, k):
+        return self._instructions()[1][k]
+
+    def instruction_output(self, k):
+        return self._instructions()[2][k]
+
+    def instruction_constant(self, k):
+        return self._instructions()[3][k]
+
+    def sz_w(self):
+        return self._instructions()[4]
+
+    def size1_out(self, i):
+        return self._outs[i].arr.shape[0]
+
+    def size2_out(self, i):
+        return self._outs[i].arr.shape[1]
 
     # -- numeric ---------------------------------------------------------------------------
     def _call_numeric(self, args):

@@ -679,3 +679,42 @@ def test_cuda_graph_step_is_bit_identical_to_the_eager_step():
                  (eager.leg_controller.command.feedfowardforce, graph.leg_controller.command.feedfowardforce)):
         assert torch.equal(a, b)
     eager.close(); graph.close()
+
+
+# ---- against the reference's CusADi GPU path (oracle/_ref, built by oracle/make_cusadi_ref.py) ------------
+def _cusadi(name, B):
+    import cusadi_ref
+    if not cusadi_ref.available(name):
+        pytest.skip(f"oracle/_ref/lib{name}.so not built (python oracle/make_cusadi_ref.py)")
+    return cusadi_ref.CusadiRefFunction(name, B, DEV)
+
+
+def test_qp_form_matches_the_cusadi_generated_kernel(batch64):
+    """The kernel the reference's generateCUDACode.py emits for qp_former (one thread per env running the whole
+    expression tape, cusadi/src/generateCUDACode.py:62-190), on the GPU, against srbd_qp_form on the same inputs."""
+    inp, _ = batch64
+    ins = _dev(inp)
+    ref = _cusadi("qp_former", len(inp[0]))
+    assert ref.evaluate(ins) > 0.0
+    _check_qp(_np(bp.qp_form(ins)), _np(ref.outputs_sparse))
+
+
+def test_pdipm_matches_the_cusadi_generated_kernel(batch64):
+    """... and for sparse_pdipm_multiple_iterations (5 iterations, 400 k instructions per env), chained like the
+    controller does (mpc_controller_cusadi.py:144-169): GPU against GPU, <= 1e-9 after the first call."""
+    inp, _ = batch64
+    B = len(inp[0])
+    qp = bp.qp_form(_dev(inp))
+    Hv, f, Av, b, Gv, d = qp
+    ref = _cusadi("sparse_pdipm_multiple_iterations", B)
+    x = torch.zeros(B, 240, dtype=torch.float64, device=DEV)
+    s = torch.maximum(d, torch.ones_like(d)); z = torch.ones_like(d); y = torch.ones(B, 140, dtype=torch.float64, device=DEV)
+    cur = None
+    for call, tol in ((1, TOL_IP), (2, 1e-8)):
+        ref.evaluate([Hv, Gv, Av, f, d, b, x, s, z, y])
+        x, s, z, y = [t.clone() for t in ref.outputs_sparse[:4]]
+        ins = [Hv, Gv, Av, f, d, b] + ([] if cur is None else list(cur[:4]))
+        cur = bp.pdipm(ins, num_iters=5, cold_start=cur is None, stage_invariant=True)
+        got, want = _np(cur), _np([x, s, z, y])
+        worst = max(rel_err(got[i][e], want[i][e]) for i in range(4) for e in range(B))
+        assert worst < tol, (call, worst)
