@@ -103,20 +103,38 @@ class ClockSampler:
 
 
 def cpu_reference_run(n_envs, iters, steps, warmup, threads, seed=20261018):
-    """Times the CPU restatement of the reference path (oracle/srbd_oracle.c: literal qp_former
-    + full-KKT sparse LDL^T PDIPM, OpenMP over envs) on a bounded sample of the workload."""
+    """Times the reference's CPU path on a bounded sample of the workload.  Preferred: oracle/_ref/lib<fn>_cpu.so, the
+    expression tapes of the reference's two functions (built from its sources by oracle/make_cusadi_ref.py) compiled to C
+    and run with `omp parallel for` over envs, the reference's own CPU convention (evaluate_parallel_cpu.cpp:79-82) --
+    kind "reference".  Otherwise the C restatement oracle/srbd_oracle.c (literal qp_former + full-KKT sparse LDL^T
+    PDIPM, OpenMP over envs) -- kind "port".  Returns (solves/s, per-step seconds, kind, description)."""
     import biped_pympc_b200 as bp
-    from oracle import c_oracle as co
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cusadi_ref
     inp, _ = bp.workload.make_batch(n_envs, seed=seed)
+    if cusadi_ref.cpu_available() and iters == 5:
+        cpu = cusadi_ref.CusadiRefCpu()
+
+        def one():
+            cpu.pdipm5(cpu.qp_former(inp, threads), threads=threads)
+        kind = "reference"
+        desc = ("oracle/_ref: expression tapes of the reference's qp_former and sparse_pdipm_multiple_iterations (its sources run over a "
+                "CasADi stand-in; CasADi itself is not installable offline) compiled to C with gcc -O1, omp parallel for over envs")
+    else:
+        from oracle import c_oracle as co
+
+        def one():
+            co.pdipm(co.qp_former(inp, nthreads=threads), iters, nthreads=threads)
+        kind = "port"
+        desc = "oracle/srbd_oracle.c (port of qp_former + full-KKT sparse LDL^T PDIPM, OpenMP over envs)"
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        qp = co.qp_former(inp, nthreads=threads)
-        co.pdipm(qp, iters, nthreads=threads)
+        one()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return n_envs / (sum(times) / len(times)), times
+    return n_envs / (sum(times) / len(times)), times, kind, desc
 
 
 def run_reference(args):
@@ -125,7 +143,7 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     sample = 2048
-    value, times = cpu_reference_run(sample, ITERS, args.steps, max(args.warmup, 1), threads)
+    value, times, kind, desc = cpu_reference_run(sample, ITERS, args.steps, max(args.warmup, 1), threads)
     ms = 1e3 * sum(times) / len(times)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -133,10 +151,8 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{ENVS_PER_GPU}-env batched SRBD MPC, 5 PDIPM iters, fp64 (BASELINE configs[1])",
                    "envs_per_step_sample": sample, "iters": ITERS, "horizon": 10},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} envs/step of the same seeded workload; oracle/srbd_oracle.c "
-                                   "(CasADi reference not installable offline: port of qp_former + full-KKT "
-                                   "sparse LDL^T PDIPM, OpenMP over envs)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{sample} envs/step of the same seeded workload; {desc}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -367,10 +383,9 @@ def run_b200(args):
         if world == 1 and default_wl:
             threads = os.cpu_count() or 1
             sample = 2048
-            cpu_val, _ = cpu_reference_run(sample, ITERS, 3, 1, threads)
-            line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{sample} envs x 3 steps of the same workload, oracle/srbd_oracle.c "
-                                              "(full-KKT sparse LDL^T, OpenMP over envs)"}
+            cpu_val, _, kind, desc = cpu_reference_run(sample, ITERS, 3, 1, threads)
+            line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "sample": f"{sample} envs x 3 steps of the same workload; {desc}"}
         sys.stdout.flush()
         if saved_stdout is not None:
             os.dup2(saved_stdout, 1)

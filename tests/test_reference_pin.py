@@ -270,3 +270,21 @@ def test_oracle_and_emulated_tick_match_the_reference_controller(refc, tick):
     assert wrench.shape == want.shape == (B, 2, 6)
     assert np.abs(wrench - want).max() <= 1e-3 * max(1.0, np.abs(want).max())
     assert np.array_equal(refc[t + "cost"], np.zeros(B, np.float32))
+
+
+def test_compiled_tapes_of_the_reference_functions_reproduce_the_fixture(ref):
+    """oracle/_ref/lib<fn>_cpu.so (oracle/make_cusadi_ref.py): the instruction streams of the reference's two functions
+    -- linearised with work-slot reuse, the view the reference's CUDA generator walks -- compiled to C.  Same graph, same
+    IEEE operations: bit-identical to the graph evaluation that produced the fixture."""
+    import cusadi_ref
+    if not cusadi_ref.cpu_available():
+        pytest.skip("oracle/_ref/lib*_cpu.so not built (python oracle/make_cusadi_ref.py --target cpu)")
+    cpu = cusadi_ref.CusadiRefCpu()
+    qp = cpu.qp_former(_inputs(ref))
+    for n, v in zip("HfAbGd", qp):
+        assert np.array_equal(v, ref[f"qp_{n}"]), n
+    out = cpu.pdipm5(qp)
+    for it in (5, 10):
+        for i, n in enumerate(("x", "s", "z", "y", "res", "mu")):
+            assert np.array_equal(out[i].reshape(ref[f"ip{it}_{n}"].shape), ref[f"ip{it}_{n}"]), (it, n)
+        out = cpu.pdipm5(qp, *out[:4])
