@@ -170,15 +170,16 @@ def run_cusadi_ref(args):
     import biped_pympc_b200 as bp
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import cusadi_ref
-    missing = [n for n in ("qp_former", "sparse_pdipm_multiple_iterations") if not cusadi_ref.available(n)]
-    if missing:
-        print(json.dumps({"impl": "cusadi", "unavailable": "oracle/_ref/lib%s.so not built (python oracle/make_cusadi_ref.py)" % missing[0]}))
+    var = cusadi_ref.solver_variant()
+    if var is None or not cusadi_ref.available("qp_former"):
+        print(json.dumps({"impl": "cusadi", "unavailable": "oracle/_ref CusADi kernels not built (python oracle/make_cusadi_ref.py)"}))
         return
+    suffix, per_call = var
     dev, B = "cuda:0", args.envs
     inp, _ = bp.workload.make_batch(B, seed=20261018)
     ins = [torch.as_tensor(a, device=dev) for a in inp]
     former = cusadi_ref.CusadiRefFunction("qp_former", B, dev)
-    solver = cusadi_ref.CusadiRefFunction("sparse_pdipm_multiple_iterations", B, dev)
+    solver = cusadi_ref.CusadiRefFunction("sparse_pdipm_multiple_iterations", B, dev, suffix)
     kern = {"qp_former": [], "solver": []}
 
     def step():
@@ -186,7 +187,12 @@ def run_cusadi_ref(args):
         Hv, f, Av, b, Gv, d = former.outputs_sparse
         x = torch.zeros(B, 240, dtype=torch.float64, device=dev)          # mpc_controller_cusadi.py:138-141
         s = torch.maximum(d, torch.ones_like(d)); z = torch.ones_like(d); y = torch.ones(B, 140, dtype=torch.float64, device=dev)
-        kern["solver"].append(solver.evaluate([Hv, Gv, Av, f, d, b, x, s, z, y]))
+        t = 0.0
+        for _ in range(ITERS // per_call):      # one call of the 5-iteration kernel, or the one-iteration build chained
+            t += solver.evaluate([Hv, Gv, Av, f, d, b, x, s, z, y])
+            if per_call != ITERS:
+                x, s, z, y = [o.clone() for o in solver.outputs_sparse[:4]]
+        kern["solver"].append(t)
 
     for _ in range(max(args.warmup, 1)):
         step()
@@ -203,7 +209,9 @@ def run_cusadi_ref(args):
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{B}-env batched SRBD MPC, 5 PDIPM iters, fp64 (BASELINE configs[1]) through the reference's CusADi-generated "
                                "kernels (its generateCUDACode.py over its function sources; expression graph from the CasADi stand-in)",
-                   "envs_per_gpu": B, "iters": ITERS},
+                   "envs_per_gpu": B, "iters": ITERS,
+                   "solver_kernel": ("the reference's 5-iteration function in one kernel" if per_call == ITERS else
+                                     "the reference's function built with num_iters=1, chained 5 x (ptxas needs > 58 GB for the 5-iteration kernel)")},
         "kernel_ms": {"qp_former": mean(kern["qp_former"]), "sparse_pdipm_multiple_iterations": mean(kern["solver"])},
         "instructions_per_env": {"qp_former": former.n_instructions, "sparse_pdipm_multiple_iterations": solver.n_instructions},
         "work_doubles_per_env": {"qp_former": former.sz_w, "sparse_pdipm_multiple_iterations": solver.sz_w}}))

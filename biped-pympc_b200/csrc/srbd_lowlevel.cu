@@ -110,10 +110,18 @@ __device__ void gait_sub_phases(float ph, int s0, int s1, int d0, int d1, float*
 __global__ void update_state_kernel(UpdateStateArgs a, int B) {
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= B) return;
-  const float* st = a.state + e * a.state_stride;
+  // all loads first (the stores below may alias them as far as the compiler knows): one round trip to L2
+  float st[33];
+  {
+    const float* g = a.state + e * a.state_stride;
+#pragma unroll
+    for (int i = 0; i < 33; ++i) st[i] = g[i];
+  }
+  const float phase = a.gait_phase[e];
+  const int s0 = a.ssp_durations[2 * e], s1 = a.ssp_durations[2 * e + 1], d0 = a.dsp_durations[2 * e], d1 = a.dsp_durations[2 * e + 1];
   // ---- gait sub-phases, leg_controller.update_gait_data ------------------------------------
   float cph[2], sph[2];
-  gait_sub_phases(a.gait_phase[e], a.ssp_durations[2 * e], a.ssp_durations[2 * e + 1], a.dsp_durations[2 * e], a.dsp_durations[2 * e + 1], cph, sph);
+  gait_sub_phases(phase, s0, s1, d0, d1, cph, sph);
 #pragma unroll
   for (int l = 0; l < 2; ++l) {
     a.contact_phase[2 * e + l] = cph[l]; a.swing_phase[2 * e + l] = sph[l];
@@ -209,14 +217,35 @@ __global__ void lowlevel_kernel(LowLevelArgs a, int B) {
   const float height = a.foot_height[e], cp1 = a.cp1[e], cp2 = a.cp2[e];
   const float fbx = clampf(0.03f * (vw.x - vdw.x), -0.3f, 0.3f), fby = clampf(0.03f * (vw.y - vdw.y), -0.3f, 0.3f);
   float action[10];
+  // all loads of both legs first (the stores below may alias them as far as the compiler knows)
+  struct LegIn { float cph, sph, rem, contact, p0[3], src[3], J[30], ff[6], q[5], qd[5]; int ssp; bool first; } in[2];
 #pragma unroll
   for (int l = 0; l < 2; ++l) {
     const long long el = e * 2 + l;
-    const float cph = a.contact_phase[el], sph = a.swing_phase[el];
-    const float dur = (float)a.ssp_durations[el] * dtm;                      // gait.swing_durations_sec
+    LegIn& L = in[l];
+    L.cph = a.contact_phase[el]; L.sph = a.swing_phase[el]; L.rem = a.swing_time_remaining[el]; L.contact = a.contact_bool[el];
+    L.ssp = a.ssp_durations[el]; L.first = a.first_swing[el] != 0;
+    const float* src = (a.world_frame ? a.foot_position : a.p) + el * 3;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { L.p0[i] = a.p0[el * 3 + i]; L.src[i] = src[i]; }
+#pragma unroll
+    for (int i = 0; i < 30; ++i) L.J[i] = a.J[el * 30 + i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) L.ff[i] = a.wrench[el * 6 + i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { L.q[i] = a.q[el * 5 + i]; L.qd[i] = a.qd[el * 5 + i]; }
+  }
+  const float phase = a.gait_phase[e];
+  const int gs0 = a.ssp_durations[2 * e], gs1 = a.ssp_durations[2 * e + 1], gd0 = a.dsp_durations[2 * e], gd1 = a.dsp_durations[2 * e + 1];
+#pragma unroll
+  for (int l = 0; l < 2; ++l) {
+    const long long el = e * 2 + l;
+    const LegIn& L = in[l];
+    const float cph = L.cph, sph = L.sph;
+    const float dur = (float)L.ssp * dtm;                          // gait.swing_durations_sec
     // ---- update_swing_time (:146-157) -----------------------------------------------------------
-    bool first = a.first_swing[el] != 0;
-    float rem = first ? dur : a.swing_time_remaining[el] - a.dt;
+    bool first = L.first;
+    float rem = first ? dur : L.rem - a.dt;
     if (cph >= 0.f) first = true;
     // ---- compute_foot_placement (:159-216) --------------------------------------------------------
     const V3 hip = v3((-0.00f + 0.0465f) - 0.06f, (l ? -1.f : 1.f) * ((0.047f + 0.015f) + 0.036f), 0.f);
@@ -227,8 +256,8 @@ __global__ void lowlevel_kernel(LowLevelArgs a, int B) {
     st3(a.foot_placement_b + el * 3, fpb);
     const V3 pf = a.world_frame ? fp : fpb;
     // ---- compute_foot_desired_position (:218-263) -----------------------------------------------
-    V3 p0 = ld3(a.p0 + el * 3);
-    if (first && sph >= 0.f) p0 = ld3((a.world_frame ? a.foot_position : a.p) + el * 3);
+    V3 p0 = ld3(L.p0);
+    if (first && sph >= 0.f) p0 = ld3(L.src);
     if (sph >= 0.f) first = false;
     if (cph >= 0.f) first = true;
     st3(a.p0 + el * 3, p0);
@@ -248,9 +277,9 @@ __global__ void lowlevel_kernel(LowLevelArgs a, int B) {
     st3(a.pDes + el * 3, pd);
     st3(a.vDes + el * 3, vd);
     // ---- leg_controller.update_command (:72-119) ---------------------------------------------------
-    const bool contact = a.contact_bool[el] != 0.f;
-    const float* J = a.J + el * 30;
-    const float* ff = a.wrench + el * 6;
+    const bool contact = L.contact != 0.f;
+    const float* J = L.J;
+    const float* ff = L.ff;
     float qdes[5];
     hector_ik(pd, l, qdes);
 #pragma unroll
@@ -264,7 +293,7 @@ __global__ void lowlevel_kernel(LowLevelArgs a, int B) {
       const float kp = contact ? 0.f : a.kp[i], kd = a.kd[i];
       a.tau[el * 5 + i] = tq; a.qDes[el * 5 + i] = qD; a.qdDes[el * 5 + i] = qdD;
       a.kpjoint[el * 5 + i] = kp; a.kdjoint[el * 5 + i] = kd;
-      const float t = tq + (kp * (qD - a.q[el * 5 + i]) + kd * (qdD - a.qd[el * 5 + i]));
+      const float t = tq + (kp * (qD - L.q[i]) + kd * (qdD - L.qd[i]));
       const float lim = a.torque_limit[5 * l + i];
       action[5 * l + i] = clampf(t, -lim, lim);
     }
@@ -272,8 +301,8 @@ __global__ void lowlevel_kernel(LowLevelArgs a, int B) {
 #pragma unroll
   for (int i = 0; i < 10; ++i) a.action[e * 10 + i] = action[i];
   if (a.advance_gait) {   // gait_generator.update_phase, same arithmetic as gait_kernel
-    const float Lf = (float)((a.dsp_durations[2 * e] + a.ssp_durations[2 * e]) + (a.dsp_durations[2 * e + 1] + a.ssp_durations[2 * e + 1]));
-    const float ph = a.gait_phase[e];
+    const float Lf = (float)((gd0 + gs0) + (gd1 + gs1));
+    const float ph = phase;
     float np = __fadd_rn(ph, __fmul_rn(__frcp_rn(__fmul_rn(Lf, dtm)), a.dt));
     np = __fsub_rn(np, np > 1.f ? 1.f : 0.f);
     a.gait_phase[e] = np;

@@ -10,7 +10,7 @@ stand-ins that close the loop:
     knots of single support, phase advanced in real time;
   * feet: a swinging foot moves linearly to a Raibert touchdown point under its hip.
 
-What it is for: parity of the hot path is unpinned (CasADi cannot run here), so a physically sane
+What it is for: next to the fixtures recorded from the reference's own code (tests/golden/), a physically sane
 closed loop -- the body stays up, tracks the commanded velocity, respects the friction cone -- is
 independent evidence that the restated formulation (signs, frames, layouts Q1/Q2 of SURVEY 8b) is
 right.  `solve(inputs17) -> x (B, 240)` is supplied by the caller: the CUDA path in the GPU test,
