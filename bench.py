@@ -159,7 +159,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def run_cusadi_ref(args):
+def run_cusadi_ref(args, emit=True):
     """`--impl cusadi`: the reference's CusADi GPU path on this GPU -- the two kernels the reference's own
     generateCUDACode.py emits (oracle/_ref, built by oracle/make_cusadi_ref.py), called the way CusadiFunction /
     MPCControllerCusadi call them: outputs and the (B, sz_w) work tensor are zero-filled before each launch
@@ -172,8 +172,10 @@ def run_cusadi_ref(args):
     import cusadi_ref
     var = cusadi_ref.solver_variant()
     if var is None or not cusadi_ref.available("qp_former"):
-        print(json.dumps({"impl": "cusadi", "unavailable": "oracle/_ref CusADi kernels not built (python oracle/make_cusadi_ref.py)"}))
-        return
+        line = {"impl": "cusadi", "unavailable": "oracle/_ref CusADi kernels not built (python oracle/make_cusadi_ref.py)"}
+        if emit:
+            print(json.dumps(line))
+        return line
     suffix, per_call = var
     dev, B = "cuda:0", args.envs
     inp, _ = bp.workload.make_batch(B, seed=20261018)
@@ -204,7 +206,7 @@ def run_cusadi_ref(args):
     torch.cuda.synchronize()
     ms = 1e3 * (time.perf_counter() - t0) / args.steps
     mean = lambda v: 1e3 * sum(v) / len(v)  # noqa: E731
-    print(json.dumps({
+    line = ({
         "impl": "cusadi", "metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{B}-env batched SRBD MPC, 5 PDIPM iters, fp64 (BASELINE configs[1]) through the reference's CusADi-generated "
@@ -214,7 +216,10 @@ def run_cusadi_ref(args):
                                      "the reference's function built with num_iters=1, chained 5 x (ptxas needs > 58 GB for the 5-iteration kernel)")},
         "kernel_ms": {"qp_former": mean(kern["qp_former"]), "sparse_pdipm_multiple_iterations": mean(kern["solver"])},
         "instructions_per_env": {"qp_former": former.n_instructions, "sparse_pdipm_multiple_iterations": solver.n_instructions},
-        "work_doubles_per_env": {"qp_former": former.sz_w, "sparse_pdipm_multiple_iterations": solver.sz_w}}))
+        "work_doubles_per_env": {"qp_former": former.sz_w, "sparse_pdipm_multiple_iterations": solver.sz_w}})
+    if emit:
+        print(json.dumps(line))
+    return line
 
 
 def run_b200(args):
@@ -394,6 +399,19 @@ def run_b200(args):
             cpu_val, _, kind, desc = cpu_reference_run(sample, ITERS, 3, 1, threads)
             line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": kind,
                                     "sample": f"{sample} envs x 3 steps of the same workload; {desc}"}
+            # the reference's CusADi GPU path on this GPU, same workload (north_star: "next to the reference's CusADi GPU
+            # path where it can be compiled offline"); see run_cusadi_ref / oracle/make_cusadi_ref.py for what it is
+            try:
+                import argparse as _ap
+                cu = run_cusadi_ref(_ap.Namespace(envs=B, steps=3, warmup=2), emit=False)
+                if "unavailable" in cu:
+                    line["cusadi_gpu_baseline"] = {"unavailable": cu["unavailable"]}
+                else:
+                    line["cusadi_gpu_baseline"] = {"value": cu["value"], "unit": UNIT, "ms_per_step": cu["ms_per_step"],
+                                                   "kernel_ms": cu["kernel_ms"], "speedup_of_this_path": value / cu["value"],
+                                                   "what": cu["config"]["workload"] + "; " + cu["config"]["solver_kernel"]}
+            except Exception as exc:      # a missing / broken baseline library must not take the bench line down
+                line["cusadi_gpu_baseline"] = {"unavailable": repr(exc)}
         sys.stdout.flush()
         if saved_stdout is not None:
             os.dup2(saved_stdout, 1)
