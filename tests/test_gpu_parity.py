@@ -724,3 +724,23 @@ def test_pdipm_matches_the_cusadi_generated_kernel(batch64):
         got, want = _np(cur), _np([x, s, z, y])
         worst = max(rel_err(got[i][e], want[i][e]) for i in range(4) for e in range(B))
         assert worst < tol, (call, worst)
+
+
+def test_general_kernel_matches_the_cusadi_kernel_on_random_values():
+    """The reference's own GPU check feeds torch.rand to every nonzero (cusadi/run_cusadi_function_test.py:15,32-41):
+    stage-varying random values on the frozen pattern, one Newton iteration, general kernel against the CusADi-generated
+    kernel of the reference function (num_iters=1 build)."""
+    import cusadi_ref
+    if not cusadi_ref.available(cusadi_ref.SOLVER, "_it1"):
+        pytest.skip("oracle/_ref/libsparse_pdipm_multiple_iterations_it1.so not built")
+    B = 33
+    g = torch.Generator(device=DEV).manual_seed(5)
+    r = lambda n, lo=0.0, hi=1.0: lo + (hi - lo) * torch.rand(B, n, dtype=torch.float64, device=DEV, generator=g)  # noqa: E731
+    ins = [r(240, 0.5, 2.0), r(280, -1, 1), r(1196, -1, 1), r(240, -1, 1), r(160, 0.5, 2), r(140, -1, 1),
+           r(240, -1, 1), r(160, 0.5, 2), r(160, 0.5, 2), r(140, -1, 1)]
+    ref = cusadi_ref.CusadiRefFunction(cusadi_ref.SOLVER, B, DEV, "_it1")
+    ref.evaluate(ins)
+    out = bp.pdipm(ins, num_iters=1, stage_invariant=False)
+    for i in range(4):
+        got, want = out[i].cpu().numpy(), ref.outputs_sparse[i].cpu().numpy()
+        assert max(rel_err(got[e], want[e]) for e in range(B)) < 1e-8, i
