@@ -225,17 +225,15 @@ class BipedControllerB200:
         return self.action
 
     def reset(self, env_ids):
-        """BipedController.reset (biped_controller.py:83-88)."""
+        """BipedController.reset (biped_controller.py:83-88) as it actually behaves: the gait phase returns to 0, the MPC
+        knot point re-anchors (first_run) and the swing controller starts a fresh swing (first_swing).  The reference
+        also calls `.zero()` on the estimator / leg data / leg command tensors, but through `tensor[env_id, ...].zero_()`
+        (core/data/robot_data.py:27-38, 108-143), which zeroes a copy made by the advanced index: those buffers -- the
+        feed-forward wrench in particular -- keep their values until the next update, here as there."""
+        import torch
         self.gait_generator.gait_phase[env_ids] = 0.0
         self.mpc_controller.reset(env_ids)
-        s, ld, c = self.state_estimator.data, self.leg_controller.data, self.leg_controller.command
-        for t in (s.root_position, s.root_euler, s.root_velocity_w, s.root_angular_velocity_w, s.foot_position, s.root_velocity_b,
-                  s.root_angular_velocity_b, ld.q, ld.qd, ld.J, ld.p, ld.v, ld.contact_phase, ld.swing_phase, c.tau, c.qDes, c.qdDes,
-                  c.pDes, c.vDes, c.feedfowardforce, c.kpjoint, c.kdjoint):
-            t[env_ids] = 0.0
-        import torch
-        s.rotation_body[env_ids] = torch.eye(3, device=self.device)
-        ld.contact_bool[env_ids] = 1.0
+        self.state_estimator.data.rotation_body[env_ids] = torch.eye(3, device=self.device)
         self.swing_leg_controller.first_swing[env_ids] = True
 
     # ---- DRL interface (mpc_wrapper.py:44-67) ----------------------------------------------------------

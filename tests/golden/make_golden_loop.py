@@ -57,7 +57,7 @@ def quat_from_euler(r, p, y):
                      cr * cp * sy - sr * sp * cy], 1)
 
 
-def main(B=B, STEPS=STEPS, reference_frame="base", gait_id=2, name="srbd_ref_loop_v1.npz", seed=20261018):
+def main(B=B, STEPS=STEPS, reference_frame="base", gait_id=2, name="srbd_ref_loop_v1.npz", seed=20261018, events=False):
     ctrl, cfg, mpc_cfg = build_reference_wrapper(B, reference_frame=reference_frame, gait_id=gait_id)
     bc = ctrl.biped_controller
     rng = np.random.default_rng(seed)
@@ -79,6 +79,19 @@ def main(B=B, STEPS=STEPS, reference_frame="base", gait_id=2, name="srbd_ref_loo
     rec = {}
     put = lambda k, v: rec.setdefault(k, []).append(np.array(v.detach().cpu().numpy() if torch.is_tensor(v) else v))  # noqa: E731
     for t in range(STEPS):
+        if events and t == 35:            # episode reset of two envs (BipedController.reset, biped_controller.py:83-88)
+            ctrl.reset(torch.tensor([1, 3]))
+            out["reset_step"], out["reset_envs"] = np.array(t), np.array([1, 3])
+        if events and t == 50:            # the RL-side knobs (mpc_wrapper.py:44-67)
+            new_dt = torch.as_tensor(rng.uniform(0.02, 0.05, B), dtype=torch.float32)
+            fh = torch.as_tensor(rng.uniform(0.05, 0.15, B), dtype=torch.float32)
+            c1 = torch.as_tensor(rng.uniform(0.2, 0.45, B), dtype=torch.float32)
+            c2 = torch.as_tensor(rng.uniform(0.55, 0.8, B), dtype=torch.float32)
+            ra = torch.as_tensor(rng.normal(0, 0.5, (2, B, 3)), dtype=torch.float32)
+            ctrl.update_mpc_sampling_time(new_dt.clone()); ctrl.set_swing_parameters(fh.clone(), c1.clone(), c2.clone())
+            ctrl.set_srbd_accel(ra[0].clone(), ra[1].clone())
+            out.update(knob_step=np.array(t), knob_dt_mpc=new_dt.numpy(), knob_foot_height=fh.numpy(), knob_cp1=c1.numpy(),
+                       knob_cp2=c2.numpy(), knob_res_lin=ra[0].numpy(), knob_res_ang=ra[1].numpy())
         qd = rng.normal(0, 0.5, (B, 10))
         q = q + 0.001 * qd + rng.normal(0, 0.002, (B, 10))
         lin_b = rng.normal(0, 0.3, (B, 3))
@@ -126,3 +139,4 @@ if __name__ == "__main__":
     main()                                                                                  # walking, base frame (defaults)
     main(B=4, STEPS=70, reference_frame="world", name="srbd_ref_loop_v1_world.npz", seed=7)  # swing targets in the world frame
     main(B=3, STEPS=30, gait_id=1, name="srbd_ref_loop_v1_standing.npz", seed=9)             # standing gait (swing time 0)
+    main(B=4, STEPS=80, name="srbd_ref_loop_v1_events.npz", seed=11, events=True)            # resets and RL-side knobs mid-run

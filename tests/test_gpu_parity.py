@@ -615,7 +615,8 @@ def test_gait_kernel_matches_the_reference_gait_generator():
 
 
 # ---- the whole control step against a recording of the reference stack ------------------------------
-@pytest.mark.parametrize("fixture", ["srbd_ref_loop_v1.npz", "srbd_ref_loop_v1_world.npz", "srbd_ref_loop_v1_standing.npz"])
+@pytest.mark.parametrize("fixture", ["srbd_ref_loop_v1.npz", "srbd_ref_loop_v1_world.npz", "srbd_ref_loop_v1_standing.npz",
+                                     "srbd_ref_loop_v1_events.npz"])
 def test_control_stack_matches_the_reference_stack(fixture):
     """tests/golden/srbd_ref_loop_v1.npz (generator tests/golden/make_golden_loop.py): 160 control steps x 6 envs
     of the reference's MPCController wrapper (gait generator, state estimator, HECTOR leg controller, swing-leg
@@ -630,7 +631,9 @@ def test_control_stack_matches_the_reference_stack(fixture):
     3e-5 N (test_controller_two_ticks_match_the_reference_controller, tests/test_reference_pin.py).  Downstream
     of the MPC the recorded wrench is injected so that the remaining quantities are compared tightly.
     `_world`: swing targets in the world frame (ControllerConf.swing_reference_frame); `_standing`: gait_id = 1,
-    whose zero swing time makes the reference divide by zero (inf / nan in vDes: reproduced position by position)."""
+    whose zero swing time makes the reference divide by zero (inf / nan in vDes: reproduced position by position);
+    `_events`: an episode reset of two envs and the RL-side knobs (update_mpc_sampling_time, set_swing_parameters,
+    set_srbd_accel: mpc_wrapper.py:44-67) changed mid-run."""
     import os
     import sys
     here = os.path.dirname(os.path.abspath(__file__))

@@ -29,6 +29,11 @@ def run(g, inject=True, dev="cuda:0"):
 
     sed, ld, cmd, sw = c.state_estimator.data, c.leg_controller.data, c.leg_controller.command, c.swing_leg_controller
     for t in range(T):
+        if "reset_step" in g and t == int(g["reset_step"]):
+            c.reset(torch.as_tensor(g["reset_envs"], device=dev))
+        if "knob_step" in g and t == int(g["knob_step"]):
+            c.update_mpc_sampling_time(D(g["knob_dt_mpc"])); c.set_swing_parameters(D(g["knob_foot_height"]), D(g["knob_cp1"]), D(g["knob_cp2"]))
+            c.set_srbd_accel(D(g["knob_res_lin"]), D(g["knob_res_ang"]))
         c.set_command(D(g["twist"][t]), D(g["height"][t]))
         c.update_state(D(g["state"][t]))
         for n in ("root_euler", "rotation_body", "root_velocity_w", "root_angular_velocity_w", "foot_position"):
