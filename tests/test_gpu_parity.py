@@ -589,7 +589,6 @@ def test_gait_kernel_matches_the_reference_gait_generator():
     fused, sep = mk(), mk()
     for gen in (fused, sep):
         gen.gait_phase[:] = torch.as_tensor(g["phase0"], device=DEV)
-    assert np.array_equal(fused.swing_durations_sec.cpu().numpy()[:0], g["swing_durations_sec"][:0])
     same = lambda a, b: np.array_equal(a, b, equal_nan=True)  # noqa: E731
     for t in range(T):
         if t == int(g["switch_step"]):
