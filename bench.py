@@ -387,6 +387,21 @@ def run_b200(args):
                             "peak_source": "DFMA micro-benchmark measured in this run (srbd_dfma_peak); "
                                            "MEASURED_PEAKS.json has no FP64 entry",
                             "algorithmic": f"{FLOP_PER_ITER:.0f} flop/iter/env x {done_iters / B:.2f} iters (mean) x {B} envs"}
+        # The resource that actually bounds the kernel (north_star: "FP64-pipe or smem-bandwidth utilisation for PDIPM"): the
+        # shared-memory data pipe moves one 128-byte wavefront per SM per clock.  Wavefronts per env-iteration come from the
+        # committed ncu capture (they do not depend on the clock or the batch), the time and the clock are this run's.
+        wf = cap.get("smem_wavefronts_per_launch")
+        clk = clocks or {}
+        if wf and clk.get("sm_mhz"):
+            sms = torch.cuda.get_device_properties(0).multi_processor_count
+            per_env_iter = wf / (4096 * 5)
+            ach_wf = per_env_iter * done_iters / (pd_ms * 1e-3) / 1e9
+            peak_wf = sms * clk["sm_mhz"] * 1e6 / 1e9
+            line["roofline_smem"] = {"kernel": "pdipm_fast_kernel<14>", "bound": "smem", "achieved": ach_wf, "peak": peak_wf,
+                                     "unit": "Gwavefront/s (128 B each)", "frac": ach_wf / peak_wf,
+                                     "wavefronts_per_env_iteration": per_env_iter,
+                                     "peak_source": f"{sms} SMs x 1 wavefront/clk x the SM clock sampled in this run ({clk['sm_mhz']:.0f} MHz)",
+                                     "source": cap.get("capture")}
         ach_bw = B * BYTES_ASSEMBLY / (fm_ms * 1e-3) / 1e9
         line["roofline_assembly"] = {"kernel": "qp_form_kernel", "bound": "hbm", "achieved": ach_bw,
                                      "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
