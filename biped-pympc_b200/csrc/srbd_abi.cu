@@ -12,6 +12,7 @@
 
 #include "../../include/srbd_mpc.h"
 #include "srbd_kernels.h"
+#include "srbd_stack_impl.h"
 
 using namespace srbd;
 

@@ -33,8 +33,8 @@ cudaError_t launch_gait(float* phase, const float* dt_mpc, const int* ssp, const
                         int horizon, float* contact_sub, float* swing_sub, int* table_i32, float* table_f32, int B,
                         cudaStream_t stream);
 // the control step around the MPC tick (srbd_lowlevel.cu); the buffers are the public srbd_loop_buffers
-struct UpdateStateArgs : srbd_loop_buffers { const float* state; int state_stride; };
-struct LowLevelArgs : srbd_loop_buffers { float kp[5], kd[5], torque_limit[10]; float dt; int world_frame, advance_gait; const float* wrench; };
+struct UpdateStateArgs;
+struct LowLevelArgs;
 cudaError_t launch_update_state(const UpdateStateArgs& a, int B, cudaStream_t stream);
 cudaError_t launch_lowlevel(const LowLevelArgs& a, int B, cudaStream_t stream);
 // DFMA micro-benchmark used for the FP64 roofline denominator

@@ -5,6 +5,7 @@
 
 #include "srbd_kernels.h"
 #include "srbd_pdipm_fast.h"
+#include "srbd_stack_impl.h"
 
 namespace srbd {
 
@@ -122,56 +123,14 @@ cudaError_t launch_marshal(const float* const* f32in12, int nQ, int fix_layout, 
 
 // State builder: compute_knot_points + set_initial_state + compute_reference_trajectory of
 // biped_pympc/convex_mpc/base_controller.py:164-257 (about 40 small fp32 torch kernels per tick in the
-// reference) as one launch.  One warp per env: lane 0 updates the open-loop knot point
-// (world_position_desired, yaw_desired, first_run) and writes x0, lanes 0..9 write one stage of x_ref each.
+// reference) as one launch, one thread per env (srbd_stack_impl.h::reference_trajectory_env): the open-loop knot point
+// (world_position_desired, yaw_desired, first_run), x0 and the ten stages of x_ref.
 // Arithmetic is fp32 with the reference's operation order and NO fused multiply-add (__fmul_rn /
 // __fadd_rn), so every entry equals what the torch expressions give, except the body->world velocity
 // (a 3x3 torch.bmm there, whose accumulation order is the BLAS back-end's): (R0 v0 + R1 v1) + R2 v2 here.
-struct RefTrajArgs {
-  const float *euler, *pos, *omega_w, *vel_w, *rot, *v_des_b, *w_des_b, *height, *dt_mpc;
-  float step;                       // cfg.decimation * cfg.dt, rounded to fp32 like torch's scalar
-  float *wpd, *yaw_des;             // (B,3), (B): in / out
-  unsigned char* first_run;         // (B) torch.bool: in / out
-  float *x0, *x_ref;                // (B,12), (B,10,12)
-};
 __global__ void reference_trajectory_kernel(RefTrajArgs a, int B) {
-  const long long e = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (e >= B) return;
-  const float px = a.pos[e * 3], py = a.pos[e * 3 + 1];
-  const float vbx = a.v_des_b[e * 3], vby = a.v_des_b[e * 3 + 1], vbz = a.v_des_b[e * 3 + 2];
-  const float wz = a.w_des_b[e * 3 + 2], h = a.height[e];
-  // knot point (base_controller.py:164-176, 221-225); every lane computes it, lane 0 stores it
-  float wx_d = a.wpd[e * 3], wy_d = a.wpd[e * 3 + 1], yaw_d = a.yaw_des[e];
-  if (a.first_run[e]) { wx_d = px; wy_d = py; yaw_d = a.euler[e * 3 + 2]; }
-  wx_d = __fadd_rn(wx_d, __fmul_rn(a.step, vbx));
-  wy_d = __fadd_rn(wy_d, __fmul_rn(a.step, vby));
-  yaw_d = __fadd_rn(yaw_d, __fmul_rn(a.step, wz));
-  __syncwarp();                                   // all lanes have read the in / out buffers
-  // desired velocity in the world frame (base_controller.py:239)
-  const float* R = a.rot + e * 9;
-  const float vwx = __fadd_rn(__fadd_rn(__fmul_rn(R[0], vbx), __fmul_rn(R[1], vby)), __fmul_rn(R[2], vbz));
-  const float vwy = __fadd_rn(__fadd_rn(__fmul_rn(R[3], vbx), __fmul_rn(R[4], vby)), __fmul_rn(R[5], vbz));
-  const bool stationary = fabsf(vbx) < 1e-2f;     // :227
-  if (lane < N) {
-    const float tb = __fmul_rn(a.dt_mpc[e], (float)lane);                      // :218
-    float4* o = reinterpret_cast<float4*>(a.x_ref + (e * N + lane) * 12);
-    const float yaw = __fadd_rn(yaw_d, __fmul_rn(wz, tb));                     // :234 (:237-238 is the same expression)
-    const float x = __fadd_rn(stationary ? wx_d : px, __fmul_rn(vwx, tb));     // :240, :245
-    const float y = __fadd_rn(stationary ? wy_d : py, __fmul_rn(vwy, tb));     // :241, :246
-    o[0] = make_float4(0.f, 0.f, yaw, x);
-    o[1] = make_float4(y, h, 0.f, 0.f);
-    o[2] = make_float4(wz, vwx, vwy, 0.f);
-  }
-  if (lane < 12) {                                 // set_initial_state, :204-211
-    const float* src = lane < 3 ? a.euler : lane < 6 ? a.pos : lane < 9 ? a.omega_w : a.vel_w;
-    a.x0[e * 12 + lane] = src[e * 3 + lane % 3];
-  }
-  if (lane == 0) {
-    a.wpd[e * 3] = wx_d; a.wpd[e * 3 + 1] = wy_d; a.wpd[e * 3 + 2] = h;     // :224
-    a.yaw_des[e] = yaw_d;
-    a.first_run[e] = 0;
-  }
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e < B) reference_trajectory_env(a, e);
 }
 
 cudaError_t launch_reference_trajectory(const float* const* f32in9, float step, float* wpd, float* yaw_des,
@@ -181,7 +140,7 @@ cudaError_t launch_reference_trajectory(const float* const* f32in9, float step, 
   a.euler = f32in9[0]; a.pos = f32in9[1]; a.omega_w = f32in9[2]; a.vel_w = f32in9[3]; a.rot = f32in9[4];
   a.v_des_b = f32in9[5]; a.w_des_b = f32in9[6]; a.height = f32in9[7]; a.dt_mpc = f32in9[8];
   a.step = step; a.wpd = wpd; a.yaw_des = yaw_des; a.first_run = first_run; a.x0 = x0; a.x_ref = x_ref;
-  reference_trajectory_kernel<<<(B + 3) / 4, 128, 0, stream>>>(a, B);
+  reference_trajectory_kernel<<<(B + 63) / 64, 64, 0, stream>>>(a, B);
   return cudaGetLastError();
 }
 
@@ -191,58 +150,9 @@ cudaError_t launch_reference_trajectory(const float* const* f32in9, float step, 
 // reference's operation order (IEEE division, no FMA): bit-exact.  Outputs are computed from the phase on
 // entry; the phase is advanced afterwards when `advance` is set (the order of BipedController.run_lowlevel,
 // biped_controller.py:120-127).
-struct GaitArgs {
-  float* phase;                  // (B) in / out
-  const float* dt_mpc;           // (B)
-  const int *ssp, *dsp;          // (B,2) single / double support durations in MPC steps [left, right]
-  float dt;
-  int advance, horizon;
-  float *contact_sub, *swing_sub;      // (B,2) or null
-  int* table_i32;                // (B,horizon,2) or null
-  float* table_f32;              // (B,horizon,2) or null
-};
 __global__ void gait_kernel(GaitArgs a, int B) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= B) return;
-  const int s0 = a.ssp[2 * e], s1 = a.ssp[2 * e + 1], d0 = a.dsp[2 * e], d1 = a.dsp[2 * e + 1];
-  const int L = (d0 + s0) + (d1 + s1);                                   // gait_cycle_length, :52
-  const float Lf = (float)L, ph = a.phase[e];
-  const float sp0 = __fdiv_rn((float)s0, Lf), sp1 = __fdiv_rn((float)s1, Lf);   // :67-68
-  const float dp0 = __fdiv_rn((float)d0, Lf), dp1 = __fdiv_rn((float)d1, Lf);
-  if (a.contact_sub) {                                                   // :99-137
-    float cl = -1.f, cr = -1.f;
-    const float th1 = __fadd_rn(sp0, dp0), th2 = __fadd_rn(th1, sp1);
-    if (ph < th1) cl = __fdiv_rn(ph, th1);
-    if (ph >= th2) cl = __fdiv_rn(__fsub_rn(ph, th2), dp0);
-    if (!(ph < sp1)) cr = __fdiv_rn(__fsub_rn(ph, sp1), __fadd_rn(__fadd_rn(dp0, sp1), dp1));
-    a.contact_sub[2 * e] = cl; a.contact_sub[2 * e + 1] = cr;
-  }
-  if (a.swing_sub) {                                                     // :139-171
-    float wl = -1.f, wr = -1.f;
-    const float st = __fadd_rn(sp1, dp0), en = __fadd_rn(st, sp0);
-    if (ph >= st && ph < en) wl = __fdiv_rn(__fsub_rn(ph, st), sp0);
-    if (ph < sp1) wr = __fdiv_rn(ph, sp1);
-    a.swing_sub[2 * e] = wl; a.swing_sub[2 * e + 1] = wr;
-  }
-  if (a.table_i32 || a.table_f32) {                                      // :215-252
-    const long long step0 = (long long)(int)__fmul_rn(ph, Lf);           // .int() truncates
-    for (int k = 0; k < a.horizon; ++k) {
-      long long g = (step0 + k) % L;
-      if (g < 0) g += L;                                                 // torch's % follows the divisor's sign
-      const bool p1 = g < s1, p2 = g >= s1 && g < s1 + d0, p3 = g >= s1 + d0 && g < s1 + d0 + s0;
-      const bool rest = !(p1 || p2 || p3);
-      const int cl = (p1 || p2 || rest) ? 1 : 0, cr = (p2 || p3 || rest) ? 1 : 0;
-      const long long o = ((long long)e * a.horizon + k) * 2;
-      if (a.table_i32) { a.table_i32[o] = cl; a.table_i32[o + 1] = cr; }
-      if (a.table_f32) { a.table_f32[o] = (float)cl; a.table_f32[o + 1] = (float)cr; }
-    }
-  }
-  if (a.advance) {                                                       // update_phase, :79-87
-    const float gds = __fmul_rn(Lf, a.dt_mpc[e]);                        // gait_durations_sec, :77
-    float np = __fadd_rn(ph, __fmul_rn(__frcp_rn(gds), a.dt));          // `dt / tensor` is tensor.reciprocal() * dt in torch
-    np = __fsub_rn(np, np > 1.f ? 1.f : 0.f);
-    a.phase[e] = np;
-  }
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e < B) gait_env(a, e);
 }
 
 cudaError_t launch_gait(float* phase, const float* dt_mpc, const int* ssp, const int* dsp, float dt, int advance,

@@ -120,3 +120,22 @@ def emul_tick(inputs17, rot, iters, tol=0.0, lane_order=1, pair=False, warm_from
                        rst.ctypes.data_as(ctypes.POINTER(ctypes.c_int)) if rst is not None else None)
     lib.srbd_emul_set_order(1)
     return outs, wrench
+
+
+_STACK_EMUL = None
+
+
+def stack_emul_lib():
+    """Host build of the small fp32 kernels around the MPC tick (csrc/srbd_stack_impl.h -> tests/emul/stack_emul.cpp)."""
+    global _STACK_EMUL
+    if _STACK_EMUL is not None:
+        return _STACK_EMUL
+    src = os.path.join(ROOT, "tests", "emul", "stack_emul.cpp")
+    out = os.path.join(ROOT, "tests", "emul", "libstack_emul.so")
+    csrc = os.path.join(ROOT, "biped-pympc_b200", "csrc")
+    deps = [src, os.path.join(csrc, "srbd_stack_impl.h"), os.path.join(ROOT, "include", "srbd_mpc.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-I", csrc, src,
+                        "-o", out], check=True)
+    _STACK_EMUL = ctypes.CDLL(out)
+    return _STACK_EMUL
