@@ -8,10 +8,10 @@
 #include "../../include/srbd_mpc.h"
 
 #ifdef __CUDACC__
-#define SRBD_HD __device__ __forceinline__
+#define SRBD_STACK_FN __device__ __forceinline__
 #else
 // host build: IEEE single-precision operations without contraction (compile with -ffp-contract=off)
-#define SRBD_HD static inline
+#define SRBD_STACK_FN static inline
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
@@ -46,20 +46,20 @@ struct LowLevelArgs : srbd_loop_buffers { float kp[5], kd[5], torque_limit[10]; 
 struct V3 { float x, y, z; };
 struct M3 { float m[9]; };   // row-major
 
-SRBD_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
-SRBD_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
-SRBD_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
-SRBD_HD V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
-SRBD_HD V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-SRBD_HD V3 mul(const M3& R, V3 v) {
+SRBD_STACK_FN V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+SRBD_STACK_FN V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+SRBD_STACK_FN V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+SRBD_STACK_FN V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+SRBD_STACK_FN V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+SRBD_STACK_FN V3 mul(const M3& R, V3 v) {
   return v3(R.m[0] * v.x + R.m[1] * v.y + R.m[2] * v.z, R.m[3] * v.x + R.m[4] * v.y + R.m[5] * v.z,
             R.m[6] * v.x + R.m[7] * v.y + R.m[8] * v.z);
 }
-SRBD_HD V3 mulT(const M3& R, V3 v) {
+SRBD_STACK_FN V3 mulT(const M3& R, V3 v) {
   return v3(R.m[0] * v.x + R.m[3] * v.y + R.m[6] * v.z, R.m[1] * v.x + R.m[4] * v.y + R.m[7] * v.z,
             R.m[2] * v.x + R.m[5] * v.y + R.m[8] * v.z);
 }
-SRBD_HD M3 mul(const M3& A, const M3& B) {
+SRBD_STACK_FN M3 mul(const M3& A, const M3& B) {
   M3 C;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -67,22 +67,22 @@ SRBD_HD M3 mul(const M3& A, const M3& B) {
     for (int j = 0; j < 3; ++j) C.m[3 * i + j] = A.m[3 * i] * B.m[j] + A.m[3 * i + 1] * B.m[3 + j] + A.m[3 * i + 2] * B.m[6 + j];
   return C;
 }
-SRBD_HD M3 rot_z(float a) {
+SRBD_STACK_FN M3 rot_z(float a) {
   float s, c;
   sincosf(a, &s, &c);
   M3 R = {{c, -s, 0.f, s, c, 0.f, 0.f, 0.f, 1.f}};
   return R;
 }
-SRBD_HD V3 col2(const M3& R) { return v3(R.m[2], R.m[5], R.m[8]); }
-SRBD_HD V3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
-SRBD_HD void st3(float* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
-SRBD_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+SRBD_STACK_FN V3 col2(const M3& R) { return v3(R.m[2], R.m[5], R.m[8]); }
+SRBD_STACK_FN V3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
+SRBD_STACK_FN void st3(float* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+SRBD_STACK_FN float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
 // HECTOR link offsets after the frame permutations of initialize_kinematics (hector.py:52-110):
 // p2 = R12p' p2, p3.. = R23p' R12p' p.. ; left leg.  The right leg mirrors y of p1, p2 and z of p3..p5.
 struct Frames { M3 R[5]; V3 p[5]; V3 p0e; };   // T01 .. T05 and the foot sole
 
-SRBD_HD void hector_fk(const float* q, int leg, Frames& F) {
+SRBD_STACK_FN void hector_fk(const float* q, int leg, Frames& F) {
   const float sy = leg ? -1.f : 1.f;
   const V3 p1 = v3(-0.00f, sy * 0.047f, -0.1265f);
   const V3 p2 = v3(0.0705f, sy * 0.015f, 0.0465f);
@@ -103,7 +103,7 @@ SRBD_HD void hector_fk(const float* q, int leg, Frames& F) {
 }
 
 // sub-phases of the gait at phase ph (same arithmetic as gait_kernel in srbd_misc.cu)
-SRBD_HD void gait_sub_phases(float ph, int s0, int s1, int d0, int d1, float* contact, float* swing) {
+SRBD_STACK_FN void gait_sub_phases(float ph, int s0, int s1, int d0, int d1, float* contact, float* swing) {
   const float Lf = (float)((d0 + s0) + (d1 + s1));
   const float sp0 = __fdiv_rn((float)s0, Lf), sp1 = __fdiv_rn((float)s1, Lf);
   const float dp0 = __fdiv_rn((float)d0, Lf), dp1 = __fdiv_rn((float)d1, Lf);
@@ -119,7 +119,7 @@ SRBD_HD void gait_sub_phases(float ph, int s0, int s1, int d0, int d1, float* co
 }
 
 
-SRBD_HD void gait_env(const GaitArgs& a, long long e) {
+SRBD_STACK_FN void gait_env(const GaitArgs& a, long long e) {
   const int s0 = a.ssp[2 * e], s1 = a.ssp[2 * e + 1], d0 = a.dsp[2 * e], d1 = a.dsp[2 * e + 1];
   const int L = (d0 + s0) + (d1 + s1);                                   // gait_cycle_length, :52
   const float Lf = (float)L, ph = a.phase[e];
@@ -163,7 +163,7 @@ SRBD_HD void gait_env(const GaitArgs& a, long long e) {
 
 
 // compute_knot_points + set_initial_state + compute_reference_trajectory for one env (base_controller.py:164-257)
-SRBD_HD void reference_trajectory_env(const RefTrajArgs& a, long long e) {
+SRBD_STACK_FN void reference_trajectory_env(const RefTrajArgs& a, long long e) {
   const float px = a.pos[e * 3], py = a.pos[e * 3 + 1];
   const float vbx = a.v_des_b[e * 3], vby = a.v_des_b[e * 3 + 1], vbz = a.v_des_b[e * 3 + 2];
   const float wz = a.w_des_b[e * 3 + 2], h = a.height[e], dtm = a.dt_mpc[e];
@@ -199,7 +199,7 @@ SRBD_HD void reference_trajectory_env(const RefTrajArgs& a, long long e) {
   a.first_run[e] = 0;
 }
 
-SRBD_HD void update_state_env(const UpdateStateArgs& a, long long e) {
+SRBD_STACK_FN void update_state_env(const UpdateStateArgs& a, long long e) {
   // all loads first (the stores below may alias them as far as the compiler knows): one round trip to L2
   float st[33];
   {
@@ -274,7 +274,7 @@ SRBD_HD void update_state_env(const UpdateStateArgs& a, long long e) {
   }
 }
 
-SRBD_HD void hector_ik(V3 p_des, int leg, float* q) {   // hector.py:234-291
+SRBD_STACK_FN void hector_ik(V3 p_des, int leg, float* q) {   // hector.py:234-291
   const float side = leg ? 1.f : -1.f;
   V3 f = p_des - v3(-0.00f + 0.0465f - 0.06f, -side * (0.047f + 0.015f), -0.126f - 0.0705f);
   f.z += 0.042f;
@@ -295,7 +295,7 @@ SRBD_HD void hector_ik(V3 p_des, int leg, float* q) {   // hector.py:234-291
   q[4] = -q[2] - q[3];
 }
 
-SRBD_HD void lowlevel_env(const LowLevelArgs& a, long long e) {
+SRBD_STACK_FN void lowlevel_env(const LowLevelArgs& a, long long e) {
   M3 R;
 #pragma unroll
   for (int i = 0; i < 9; ++i) R.m[i] = a.rotation_body[9 * e + i];
