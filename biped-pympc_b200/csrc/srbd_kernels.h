@@ -37,6 +37,9 @@ struct UpdateStateArgs;
 struct LowLevelArgs;
 cudaError_t launch_update_state(const UpdateStateArgs& a, int B, cudaStream_t stream);
 cudaError_t launch_lowlevel(const LowLevelArgs& a, int B, cudaStream_t stream);
+// host entry: one chunk of inputs from mapped pinned host memory into device staging, co-resident with a running solve
+cudaError_t launch_prefetch(const double* const* src, double* const* dst, const int* n, const float* rot_src, float* rot_dst,
+                            int rot_n, int ctas, cudaStream_t stream);
 // DFMA micro-benchmark used for the FP64 roofline denominator
 cudaError_t launch_dfma_peak(double* sink, int iters, int blocks, int threads, cudaStream_t stream);
 

@@ -166,6 +166,36 @@ cudaError_t launch_gait(float* phase, const float* dt_mpc, const int* ssp, const
   return cudaGetLastError();
 }
 
+// Host-entry prefetch: pulls one chunk of the 17 qp_former inputs (+ the rotation) from mapped pinned host memory into
+// the context's device staging area with plain loads over PCIe.  It needs no shared memory and few registers, so its CTAs
+// co-reside with the solve kernel of the previous chunk (which holds one 226 KB CTA per SM) and the transfer hides behind
+// that solve -- what the copy engine (cudaMemcpyAsync, 16 calls per chunk) did not achieve.
+struct PrefetchArgs {
+  const double* src[QP_N_IN];
+  double* dst[QP_N_IN];
+  int n[QP_N_IN];                 // doubles per array for this chunk (0 = skip)
+  const float* rot_src; float* rot_dst; int rot_n;
+};
+__global__ void __launch_bounds__(128) prefetch_kernel(PrefetchArgs a) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+#pragma unroll 1
+  for (int i = 0; i < QP_N_IN; ++i) {
+    const double* __restrict__ s = a.src[i];     // 8-byte accesses: no alignment assumption on the caller's buffers
+    double* __restrict__ d = a.dst[i];
+    for (int k = tid; k < a.n[i]; k += nthr) d[k] = s[k];
+  }
+  for (int k = tid; k < a.rot_n; k += nthr) a.rot_dst[k] = a.rot_src[k];
+}
+
+cudaError_t launch_prefetch(const double* const* src, double* const* dst, const int* n, const float* rot_src, float* rot_dst,
+                            int rot_n, int ctas, cudaStream_t stream) {
+  PrefetchArgs a;
+  for (int i = 0; i < QP_N_IN; ++i) { a.src[i] = src[i]; a.dst[i] = dst[i]; a.n[i] = (src[i] && dst[i]) ? n[i] : 0; }
+  a.rot_src = rot_src; a.rot_dst = rot_dst; a.rot_n = rot_n;
+  prefetch_kernel<<<ctas, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
 // 8 independent DFMA chains per thread; 16 flop per inner iteration per thread.
 __global__ void dfma_peak_kernel(double* sink, int iters) {
   double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
