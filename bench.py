@@ -324,7 +324,7 @@ def run_b200(args):
                    "envs_per_gpu": B, "iters": args.calls * args.iters, "horizon": 10, "parallelism": f"env-sharded x{world}, no collective",
                    "l2": "256 MB buffer written between timed iterations (L2 flush)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": n_e2e, "api": "srbd_mpc_solve_host (pinned host buffers read and written in place over PCIe by the kernels; two 2058-env chunks on two streams)"},
+                "steps": n_e2e, "api": "srbd_mpc_solve_host (pinned host buffers read and written over PCIe by the kernels themselves: the first 2058-env chunk in place, the second pulled into device staging by a co-resident prefetch kernel while the first solves)"},
         "gpu_launches": args.steps,          # ONE kernel per step: fused assembly + PDIPM + wrench (pdipm_fast_kernel)
         "clocks": clocks,
     }
