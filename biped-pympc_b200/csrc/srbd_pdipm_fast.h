@@ -168,7 +168,10 @@ struct PdipmFast {
 #pragma unroll
       for (int a = 0; a < 4; ++a) { c0[a] = 0.0; c1[a] = 0.0; }
 #pragma unroll
-      for (int a = 0; a < 3; ++a) { i0[a] = q; i1[a] = q; }
+      // slots with a zero coefficient point where the lanes with a real entry point (rows 6 + a / a):
+      // every distinct address of a lane-varying shared-memory load costs wavefronts
+      // (profiles/smem_bcast_r1_wavefronts.csv)
+      for (int a = 0; a < 3; ++a) { i0[a] = 6 + a; i1[a] = a; }
       c0[0] = A[q] * ph[q];
       c1[0] = A[q] * ph[q];
       if (q < 3) {
@@ -319,7 +322,7 @@ struct PdipmFast {
   // rho_k (into vy) from r1~ (vx) and the equality right-hand sides held in vy;
   // cor: corrector right-hand side (r1x = r4 = 0: only the input part of r1~ is non-zero)
   // ------------------------------------------------------------------------------------
-  SRBD_DEV void build_rho(int k, bool cor) const {
+  SRBD_DEV void build_rho(int k, bool cor, const double Brow[12]) const {
     double* vx = sm + SM::OFF_VX;
     double* vy = sm + SM::OFF_VY;
     double* b = bc();
@@ -332,7 +335,7 @@ struct PdipmFast {
     {
       double bv[12];
       ld12(b, bv);
-      double rho = brow_dot(bv);
+      double rho = dot12(Brow, bv);
       if (!cor) {
         rho += phx_rr * vx[12 * k + rr] + vy[12 * k + rr];
         if (k >= 1) {
@@ -638,11 +641,17 @@ struct PdipmFast {
 #endif
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
+        {
+          // the lane's row of Bbar stays in registers for the five stages: a lane-varying row load costs
+          // twice the wavefronts of a broadcast (profiles/smem_bcast_r1_wavefronts.csv)
+          double Brow[12];
+          ld12(fb() + FB_B + 14 * rr, Brow);
 #pragma unroll 1
-        for (int t = 0; t < 5; ++t) {
-          const int k = h ? 9 - t : t;
-          if (pass == 1) corrector_rhs(k, smu);
-          build_rho(k, pass == 1);
+          for (int t = 0; t < 5; ++t) {
+            const int k = h ? 9 - t : t;
+            if (pass == 1) corrector_rhs(k, smu);
+            build_rho(k, pass == 1, Brow);
+          }
         }
         if (pass == 0) {
           SRBD_TRACE("rho_aff", vy, 140);
@@ -761,6 +770,8 @@ struct PdipmFast {
     const int jj = r & 7, ft = r >> 3;
     const double valid = r < 12 ? 1.0 : 0.0;
     double a_sz = 0, a_rs = 0, a_rx = 0, a_re = 0;
+    double Brow[12];
+    ld12(f + FB_B + 14 * rr, Brow);
 #pragma unroll 1
     for (int t = 0; t < 5; ++t) {
       const int k = h ? 9 - t : t;
@@ -830,7 +841,7 @@ struct PdipmFast {
         // dynamics row rr
         double uv[12];
         ld12(u, uv);
-        double re = sx[12 * k + rr] - bd + brow_dot(uv);
+        double re = sx[12 * k + rr] - bd + dot12(Brow, uv);
         if (k >= 1) {
           const double* xp = xs + 12 * (k - 1);
           re += c0[0] * xp[rr] + c0[1] * xp[i0[0]] + c0[2] * xp[i0[1]] + c0[3] * xp[i0[2]];
