@@ -306,9 +306,19 @@ struct PdipmFast {
   }
   // column rr of Bbar times the 12-vector at v (shared memory)
   SRBD_DEV double bcol_dot(const double* v) const {
+    double bc8[8];
+    ld_bcol(bc8);
+    return bcol_dot(bc8, v);
+  }
+  // the eight structural non-zeros of column rr of Bbar (kept in registers over a stage loop)
+  SRBD_DEV void ld_bcol(double bc8[8]) const {
     const double* B = fb() + FB_B + rr;
-    const double q0 = B[0] * v[0] + B[14] * v[1] + B[28] * v[2] + B[14 * bs0] * v[bs0];
-    const double q1 = B[84] * v[6] + B[98] * v[7] + B[112] * v[8] + B[14 * bs1] * v[bs1];
+    bc8[0] = B[0]; bc8[1] = B[14]; bc8[2] = B[28]; bc8[3] = B[14 * bs0];
+    bc8[4] = B[84]; bc8[5] = B[98]; bc8[6] = B[112]; bc8[7] = B[14 * bs1];
+  }
+  SRBD_DEV double bcol_dot(const double bc8[8], const double* v) const {
+    const double q0 = bc8[0] * v[0] + bc8[1] * v[1] + bc8[2] * v[2] + bc8[3] * v[bs0];
+    const double q1 = bc8[4] * v[6] + bc8[5] * v[7] + bc8[6] * v[8] + bc8[7] * v[bs1];
     return q0 + q1;
   }
   // row rr of Bbar times the 12-vector v
@@ -661,8 +671,12 @@ struct PdipmFast {
         solve_thomas();
         if (pass == 0) SRBD_TRACE("dyd_aff", vy, 120);
         mn_s = 1e300; mn_z = 1e300;   // min over ALL 160 candidates (1.0 where dv >= 0): may exceed 1
+        {
+          double bc8[8];
+          ld_bcol(bc8);
 #pragma unroll 1
-        for (int t = 0; t < 5; ++t) recover(h ? 9 - t : t, pass, mn_s, mn_z);
+          for (int t = 0; t < 5; ++t) recover(h ? 9 - t : t, pass, bc8, mn_s, mn_z);
+        }
         if (pass == 0) {
           w.sync();
           double* ws = gws();
@@ -882,7 +896,7 @@ struct PdipmFast {
   }
 
   // recover dx, du (into vx), dy_mx (into vy) and this lane's ds / dz of inequality row 16k + r
-  SRBD_DEV void recover(int k, int pass, double& mn_s, double& mn_z) const {
+  SRBD_DEV void recover(int k, int pass, const double bc8[8], double& mn_s, double& mn_z) const {
     const double* f = fb();
     double* vx = sm + SM::OFF_VX;
     double* vy = sm + SM::OFF_VY;
@@ -893,7 +907,7 @@ struct PdipmFast {
     double* b = bc();
     double* vu = vx + 120 + 12 * k;
     const double* dyk = vy + 12 * k;
-    b[rr] = vu[rr] - bcol_dot(dyk);
+    b[rr] = vu[rr] - bcol_dot(bc8, dyk);
     w.sync();
     {
       double du = psi_apply(psi(k), b);

@@ -126,7 +126,7 @@ struct PdipmPair {
 #pragma unroll
     for (int a = 0; a < 4; ++a) { X.c0[a] = 0.0; X.c1[a] = 0.0; }
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { X.i0[a] = q; X.i1[a] = q; }
+    for (int a = 0; a < 3; ++a) { X.i0[a] = 6 + a; X.i1[a] = a; }   // zero-coefficient slots share an address (srbd_pdipm_fast.h)
     X.c0[0] = A[q] * ph[q];
     X.c1[0] = A[q] * ph[q];
     if (q < 3) {
