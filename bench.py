@@ -405,7 +405,10 @@ def run_b200(args):
         ach_bw = B * BYTES_ASSEMBLY / (fm_ms * 1e-3) / 1e9
         line["roofline_assembly"] = {"kernel": "qp_form_kernel", "bound": "hbm", "achieved": ach_bw,
                                      "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                                     "frac": ach_bw / peaks.get("hbm_gbs", 6650.0), "traffic": None,
+                                     "frac": ach_bw / peaks.get("hbm_gbs", 6650.0),
+                                     "traffic": cap.get("assembly_dram_bytes_per_launch"),
+                                     "traffic_note": "DRAM bytes of one launch from profiles/ncu_qpform_r1_4096_summary.csv: below the "
+                                                     f"{B * BYTES_ASSEMBLY} algorithmic bytes because most of the output is still in L2 at kernel end",
                                      "kernel_ms": fm_ms, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)"}
         # ---- CPU baseline on the box's host cores (bounded sample) -----------------------------
         if world == 1 and default_wl:
