@@ -18,7 +18,8 @@ QP_NNZ_IN = (12, 120, 120, 120, 1, 1, 1, 9, 9, 3, 3, 3, 20, 12, 12, 3, 3)
 QP_NNZ_OUT = (240, 240, 1196, 140, 280, 160)
 IP_NNZ_IN = (240, 280, 1196, 240, 160, 140, 240, 160, 160, 140)
 IP_NNZ_OUT = (240, 160, 160, 140, 4, 1)
-WORK_DOUBLES = 6224
+WORK_DOUBLES = 6224          # general kernel, per env (srbd_args.h PDIPM_WORK_DOUBLES)
+WORK_DOUBLES_FAST = 1024     # fast kernel (STAGE_INVARIANT), per env
 
 _lib = None
 _P = ctypes.POINTER(ctypes.c_double)
@@ -58,7 +59,7 @@ def load(build_if_missing: bool = True):
                                  ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
     lib.srbd_qp_form.argtypes = [vp, vp, ci, vp]
     lib.srbd_pdipm_work_doubles.restype = ctypes.c_size_t
-    lib.srbd_pdipm_work_doubles.argtypes = [ci]
+    lib.srbd_pdipm_work_doubles.argtypes = [ci, cu]
     lib.srbd_pdipm.argtypes = [vp, vp, vp, vp, ci, ci, cd, cu, vp]
     lib.srbd_pdipm_is_stage_invariant.argtypes = [vp, ci, vp, ctypes.POINTER(ci)]
     lib.srbd_marshal_inputs.argtypes = [vp, ci, ci, ci, cd, cd, vp, ci, vp]
@@ -137,6 +138,26 @@ def _check_inputs(tensors, nnz, B=None, device_type="cuda"):
     return out, B
 
 
+def _check_buffers(what, tensors, nnz, B, dev, dtype=None):
+    """Caller-provided output / scratch tensors: dtype, device, contiguity and room for B envs.  The kernels write
+    B * nnz elements whatever the tensor's own shape says, so a short buffer would be a silent out-of-bounds write."""
+    import torch
+    dtype = dtype or torch.float64
+    if len(tensors) != len(nnz):
+        raise ValueError(f"{what}: expected {len(nnz)} tensors, got {len(tensors)}")
+    for i, (t, n) in enumerate(zip(tensors, nnz)):
+        if t is None:
+            continue
+        if t.dtype != dtype:
+            raise TypeError(f"{what}[{i}]: expected {dtype}, got {t.dtype}")
+        if t.device != dev:
+            raise ValueError(f"{what}[{i}]: expected a tensor on {dev}, got {t.device}")
+        if not t.is_contiguous():
+            raise ValueError(f"{what}[{i}]: must be contiguous")
+        if t.numel() < B * n:
+            raise ValueError(f"{what}[{i}]: needs {B} x {n} elements, has {t.numel()}")
+
+
 def qp_form(inputs: Sequence, out: Optional[List] = None) -> List:
     """qp_former: 17 (B, nnz) fp64 CUDA tensors -> [H, f, A, b, G, d] CCS value tensors."""
     import torch
@@ -145,6 +166,8 @@ def qp_form(inputs: Sequence, out: Optional[List] = None) -> List:
     dev = ins[0].device
     if out is None:
         out = [torch.empty((B, n), dtype=torch.float64, device=dev) for n in QP_NNZ_OUT]
+    else:
+        _check_buffers("qp_form out", out, QP_NNZ_OUT, B, dev)
     with torch.cuda.device(dev):
         check(lib.srbd_qp_form(_ptr_array(ins), _ptr_array(out), B, _stream()))
     return out
@@ -165,9 +188,22 @@ def marshal(f32_tensors: Sequence, mass: float, mu: float, fix_layout=False, q_s
     if len(ts) != 12:
         raise ValueError("marshal: expected 12 tensors")
     B, dev = ts[0].shape[0], ts[0].device
+    # per-env element counts of the 12 inputs (Q and R are shared by all envs): B comes from x0 alone, so check the rest
+    per_env = (12, 120, 9, 9, 3, 6, 20, 1, None, None, 3, 3)
+    for i, (t, n) in enumerate(zip(ts, per_env)):
+        if t.device != dev:
+            raise ValueError(f"marshal: argument {i} is on {t.device}, expected {dev}")
+        if n is not None and t.numel() < B * n:
+            raise ValueError(f"marshal: argument {i} needs {B} x {n} elements, has {t.numel()}")
+    if ts[8].numel() < 12 or ts[9].numel() < 12:
+        raise ValueError("marshal: Q and R need at least 12 entries")
     if out is None:
         out = [torch.empty((B, n), dtype=torch.float64, device=dev) if (with_linearisation_point or i not in (1, 2)) else None
                for i, n in enumerate(QP_NNZ_IN)]
+    else:
+        _check_buffers("marshal out", out, QP_NNZ_IN, B, dev)
+        if any(out[i] is None for i in range(len(QP_NNZ_IN)) if i not in (1, 2)):
+            raise ValueError("marshal out: only entries 1 and 2 (x, u) may be None")
     with torch.cuda.device(dev):
         check(lib.srbd_marshal_inputs(_ptr_array(ts), int(ts[8].numel()), int(bool(fix_layout)), int(bool(q_stride_bug)),
                                       float(mass), float(mu), _ptr_array(out, allow_none=True), B, _stream()))
@@ -236,9 +272,18 @@ def pdipm(inputs: Sequence, num_iters: int = 5, tol: float = 0.0, cold_start: bo
     dev = chk[0].device
     if out is None:
         out = [torch.empty((B, n), dtype=torch.float64, device=dev) for n in IP_NNZ_OUT]
-    if work is None:
-        work = torch.empty((B, WORK_DOUBLES), dtype=torch.float64, device=dev)
+    else:
+        _check_buffers("pdipm out", out, IP_NNZ_OUT, B, dev)
+        if any(o is None for o in out):
+            raise ValueError("pdipm out: all six output tensors are required")
     flags = (COLD_START if cold_start else 0) | (STAGE_INVARIANT if stage_invariant else 0)
+    per_env = WORK_DOUBLES_FAST if stage_invariant else WORK_DOUBLES     # = srbd_pdipm_work_doubles(1, flags)
+    if work is None:
+        work = torch.empty((B, per_env), dtype=torch.float64, device=dev)
+    else:
+        _check_buffers("pdipm work", [work], [per_env], B, dev)
+    if iters_done is not None:
+        _check_buffers("pdipm iters_done", [iters_done], [1], B, dev, dtype=torch.int32)
     with torch.cuda.device(dev):
         check(lib.srbd_pdipm(_ptr_array(ins, allow_none=True), _ptr_array(out), ctypes.c_void_p(work.data_ptr()),
                              ctypes.c_void_p(iters_done.data_ptr()) if iters_done is not None else None,
@@ -294,7 +339,13 @@ class Context:
         import torch
         lib = load()
         ins, B, dev = _check_qp_inputs(inputs17)
+        if B > self.max_B:
+            raise ValueError(f"Context.solve: batch of {B} envs exceeds the context's max_B = {self.max_B}")
         rot = rotation_body.to(torch.float32).contiguous()
+        if rot.numel() < B * 9 or rot.device != dev:
+            raise ValueError("Context.solve: rotation_body must hold B x 9 elements on the inputs' device")
+        if iters_done is not None:
+            _check_buffers("Context.solve iters_done", [iters_done], [1], B, dev, dtype=torch.int32)
         w = torch.empty((B, 2, 6), dtype=torch.float32, device=dev)
         extra = [None] * 5
         if want_iterates:
@@ -330,8 +381,24 @@ class Context:
         """HOST (ideally pinned) tensors in/out; H2D + kernels + D2H; synchronous.
         inputs17_host[1] / [2] (x, u: the linearisation point) may be None = all ones, the constant
         the reference call site uses (mpc_controller_cusadi.py:55-56); they are then not copied."""
+        import torch
         lib = load()
         B = inputs17_host[0].shape[0]
+        if B > self.max_B:
+            raise ValueError(f"Context.solve_host: batch of {B} envs exceeds the context's max_B = {self.max_B}")
+        for i, (t, n) in enumerate(zip(inputs17_host, QP_NNZ_IN)):
+            if t is None:
+                if i not in (1, 2):
+                    raise ValueError(f"solve_host: input {i} is required")
+                continue
+            if t.dtype != torch.float64 or t.device.type != "cpu" or not t.is_contiguous() or t.numel() != B * n:
+                raise ValueError(f"solve_host: input {i} must be a contiguous float64 host tensor of {B} x {n} elements")
+        for name, t, n, dt in (("rotation_body_host", rotation_body_host, 9, torch.float32), ("wrench_host", wrench_host, 12, torch.float32),
+                               ("x_out_host", x_out_host, 240, torch.float64), ("res_out_host", res_out_host, 4, torch.float64)):
+            if t is None and name in ("x_out_host", "res_out_host"):
+                continue
+            if t.dtype != dt or t.device.type != "cpu" or not t.is_contiguous() or t.numel() < B * n:
+                raise ValueError(f"solve_host: {name} must be a contiguous {dt} host tensor with room for {B} x {n} elements")
         ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
         check(lib.srbd_mpc_solve_host(self._h, _ptr_array(inputs17_host, allow_none=True), ptr(rotation_body_host), B,
                                       int(num_calls), int(iters_per_call), float(tol), ptr(wrench_host),

@@ -92,6 +92,31 @@ int ensure_init() {
 }
 int num_sms() { int dev = 0; cudaGetDevice(&dev); return g_num_sms[dev] > 0 ? g_num_sms[dev] : 148; }
 
+// Per-device state of the synchronous entries (the probe and the CusADi-compatible `evaluate`): a flag word, a small
+// pinned host area for the pointer tables / the flag, and the PDIPM scratch, grown on demand and never freed per
+// call.  One mutex per device serialises the callers that share it.
+struct CompatWs {
+  std::mutex mu;
+  int* flag = nullptr;          // device
+  void** host = nullptr;        // pinned: [0] flag read-back, [1..] pointer tables
+  double* work = nullptr;       // device, work_doubles doubles
+  size_t work_doubles = 0;
+};
+CompatWs g_compat[64];
+CompatWs* compat_ws() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  CompatWs* ws = &g_compat[dev];
+  std::lock_guard<std::mutex> lk(ws->mu);
+  if (!ws->flag) {
+    if (cudaMalloc((void**)&ws->flag, sizeof(int)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaHostAlloc((void**)&ws->host, 64 * sizeof(void*), cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError(); cudaFree(ws->flag); ws->flag = nullptr; return nullptr;
+    }
+  }
+  return ws;
+}
+
 }  // namespace
 
 struct srbd_ctx {
@@ -101,7 +126,7 @@ struct srbd_ctx {
   double* it[4] = {nullptr};              // x s z y
   double* res = nullptr;                  // (B,4)
   double* mu = nullptr;                   // (B,1)
-  double* work = nullptr;                 // (B, PDIPM_WORK_DOUBLES)
+  double* work = nullptr;                 // (B, PDIPM_WORK_DOUBLES_FAST): the tick only runs the fast kernel
   double* in_stage[QP_N_IN] = {nullptr};  // device copies of host inputs (host entry only)
   float* rot_stage = nullptr;
   float* wrench_stage = nullptr;
@@ -156,9 +181,16 @@ int srbd_pattern(char which, const int** colptr, const int** row, int* nrow, int
   return SRBD_OK;
 }
 
+namespace {
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+}  // namespace
+
 int srbd_qp_form(const double* const* in17, double* const* out6, int B, void* stream) {
   if (!in17 || !out6 || B < 0) return SRBD_EINVAL;
   if (B == 0) return SRBD_OK;
+  // the kernel moves x, u, x_ref and all six outputs as 16-byte vectors (alignment contract of include/srbd_mpc.h)
+  for (int i = 0; i < QP_N_OUT; ++i) if (!aligned16(out6[i])) return SRBD_EINVAL;
+  if (!aligned16(in17[IN_X]) || !aligned16(in17[IN_U]) || !aligned16(in17[IN_XREF])) return SRBD_EINVAL;
   int rc = ensure_init();
   if (rc) return rc;
   QpFormArgs a;
@@ -170,7 +202,10 @@ int srbd_qp_form(const double* const* in17, double* const* out6, int B, void* st
   return SRBD_OK;
 }
 
-size_t srbd_pdipm_work_doubles(int B) { return B > 0 ? (size_t)B * PDIPM_WORK_DOUBLES : 0; }
+size_t srbd_pdipm_work_doubles(int B, unsigned flags) {
+  if (B <= 0) return 0;
+  return (size_t)B * ((flags & SRBD_STAGE_INVARIANT) ? PDIPM_WORK_DOUBLES_FAST : PDIPM_WORK_DOUBLES);
+}
 
 int srbd_pdipm(const double* const* in10, double* const* out6, double* work, int* iters_done,
                int B, int num_iters, double tol, unsigned flags, void* stream) {
@@ -186,10 +221,12 @@ int srbd_pdipm(const double* const* in10, double* const* out6, double* work, int
     a.in[i] = in10[i];
   }
   for (int i = 0; i < IP_N_OUT; ++i) { if (!out6[i]) return SRBD_EINVAL; a.out[i] = out6[i]; }
-  a.work = work; a.iters_done = iters_done; a.num_iters = num_iters; a.tol = tol; a.cold_start = cold ? 1 : 0;
+  const bool fast = (flags & SRBD_STAGE_INVARIANT) != 0;
+  a.work = work; a.work_stride = fast ? PDIPM_WORK_DOUBLES_FAST : PDIPM_WORK_DOUBLES; a.inv_flag = nullptr;
+  a.iters_done = iters_done; a.num_iters = num_iters; a.tol = tol; a.cold_start = cold ? 1 : 0;
   a.fused = 0; a.rot = nullptr; a.wrench = nullptr; a.warm_xy = 0; a.reset = nullptr;
   for (int i = 0; i < QP_N_IN; ++i) a.qp_in[i] = nullptr;
-  SRBD_CUDA(launch_pdipm(a, B, (flags & SRBD_STAGE_INVARIANT) != 0, num_sms(), (cudaStream_t)stream));
+  SRBD_CUDA(launch_pdipm(a, B, fast, num_sms(), (cudaStream_t)stream));
   return SRBD_OK;
 }
 
@@ -199,17 +236,16 @@ int srbd_pdipm_is_stage_invariant(const double* const* in10, int B, void* stream
   if (B == 0) return SRBD_OK;
   int rc = ensure_init();
   if (rc) return rc;
-  int* flag = nullptr;
-  SRBD_CUDA(cudaMalloc((void**)&flag, sizeof(int)));
+  CompatWs* ws = compat_ws();             // per-device flag word: nothing is allocated per call
+  if (!ws) return SRBD_ENOMEM;
+  std::lock_guard<std::mutex> lk(ws->mu);
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), st);
-  if (e == cudaSuccess) e = launch_stage_invariant_probe(in10[IP_Q], in10[IP_G], in10[IP_A], flag, B, st);
-  int h = 1;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaMemsetAsync(ws->flag, 0, sizeof(int), st);
+  if (e == cudaSuccess) e = launch_stage_invariant_probe(in10[IP_Q], in10[IP_G], in10[IP_A], ws->flag, B, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ws->host, ws->flag, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(flag);
   if (e != cudaSuccess) return cuda_fail(e);
-  *result = (h == 0);
+  *result = (*(volatile int*)ws->host == 0);
   return SRBD_OK;
 }
 
@@ -329,7 +365,7 @@ int srbd_ctx_create(srbd_ctx** out, int max_B, int device) {
   for (int i = 0; i < 4; ++i) alloc((void**)&c->it[i], B * itn[i] * sizeof(double));
   alloc((void**)&c->res, B * 4 * sizeof(double));
   alloc((void**)&c->mu, B * sizeof(double));
-  alloc((void**)&c->work, B * PDIPM_WORK_DOUBLES * sizeof(double));
+  alloc((void**)&c->work, B * PDIPM_WORK_DOUBLES_FAST * sizeof(double));
   for (int i = 0; i < QP_N_IN; ++i) alloc((void**)&c->in_stage[i], B * kQpNnzIn[i] * sizeof(double));
   alloc((void**)&c->rot_stage, B * 9 * sizeof(float));
   alloc((void**)&c->wrench_stage, B * 12 * sizeof(float));
@@ -368,7 +404,8 @@ int solve_range(srbd_ctx* c, const double* const* in17, const float* rotation_bo
       a.qp_in[i] = in17[i];
     }
     a.out[IPO_X] = x; a.out[IPO_S] = s; a.out[IPO_Z] = z; a.out[IPO_Y] = y; a.out[IPO_RES] = res; a.out[IPO_MU] = c->mu + o;
-    a.work = c->work + o * PDIPM_WORK_DOUBLES; a.iters_done = iters_done; a.num_iters = iters; a.tol = tol;
+    a.work = c->work + o * PDIPM_WORK_DOUBLES_FAST; a.work_stride = PDIPM_WORK_DOUBLES_FAST; a.inv_flag = nullptr;
+    a.iters_done = iters_done; a.num_iters = iters; a.tol = tol;
     a.cold_start = 1; a.fused = 1; a.rot = rotation_body; a.wrench = wrench;
     a.warm_xy = warm ? 1 : 0; a.reset = reset;
     SRBD_CUDA(launch_pdipm(a, B, true, num_sms(), st));
@@ -381,7 +418,7 @@ int solve_range(srbd_ctx* c, const double* const* in17, const float* rotation_bo
   const double* in10[IP_N_IN] = {qp[OUT_H], qp[OUT_G], qp[OUT_A], qp[OUT_F], qp[OUT_D], qp[OUT_B],
                                  nullptr, nullptr, nullptr, nullptr};
   double* out6[IP_N_OUT] = {x, s, z, y, res, c->mu + o};
-  rc = srbd_pdipm(in10, out6, c->work + o * PDIPM_WORK_DOUBLES, iters_done, B, iters, tol,
+  rc = srbd_pdipm(in10, out6, c->work + o * PDIPM_WORK_DOUBLES_FAST, iters_done, B, iters, tol,
                   SRBD_COLD_START | SRBD_STAGE_INVARIANT, st);
   if (rc) return rc;
   if (wrench) return srbd_wrench(x, rotation_body, wrench, B, st);
@@ -453,6 +490,9 @@ int srbd_mpc_solve_host(srbd_ctx* c, const double* const* in17_host, const float
   int chunk = (zero_copy ? 147 : 74) * per_cta;     // 2 058 / 1 036 envs
   if (const char* ev = std::getenv("SRBD_HOST_CHUNK")) chunk = std::atoi(ev) > 0 ? std::atoi(ev) : chunk;   // tuning knob
   if (B <= chunk) chunk = B;
+  // Any failure inside the loop leaves the loop (never returns from it): earlier chunks may still be in flight on the
+  // two internal streams, reading and writing the caller's host buffers, so both streams are drained before returning.
+#define HOST_TRY(expr) { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { rc = cuda_fail(e__); break; } }
   int rc = SRBD_OK, ci = 0;
   for (int e0 = 0; e0 < B; e0 += chunk, ++ci) {
     const int nb = (B - e0 < chunk) ? B - e0 : chunk;
@@ -473,7 +513,7 @@ int srbd_mpc_solve_host(srbd_ctx* c, const double* const* in17_host, const float
         n[i] = nb * kQpNnzIn[i];
         din[i] = dst[i];
       }
-      SRBD_CUDA(launch_prefetch(src, dst, n, zrot + o * 9, c->rot_stage + o * 9, nb * 9, num_sms(), st));
+      HOST_TRY(launch_prefetch(src, dst, n, zrot + o * 9, c->rot_stage + o * 9, nb * 9, num_sms(), st));
       drot = c->rot_stage + o * 9;
       dw = zw + o * 12;
     } else if (zero_copy) {
@@ -484,10 +524,11 @@ int srbd_mpc_solve_host(srbd_ctx* c, const double* const* in17_host, const float
       for (int i = 0; i < QP_N_IN; ++i) {
         if (!in17_host[i]) { din[i] = nullptr; continue; }
         din[i] = c->in_stage[i] + o * kQpNnzIn[i];
-        SRBD_CUDA(cudaMemcpyAsync(c->in_stage[i] + o * kQpNnzIn[i], in17_host[i] + o * kQpNnzIn[i],
+        HOST_TRY(cudaMemcpyAsync(c->in_stage[i] + o * kQpNnzIn[i], in17_host[i] + o * kQpNnzIn[i],
                                   (size_t)nb * kQpNnzIn[i] * sizeof(double), cudaMemcpyHostToDevice, st));
       }
-      SRBD_CUDA(cudaMemcpyAsync(c->rot_stage + o * 9, rotation_body_host + o * 9, (size_t)nb * 9 * sizeof(float),
+      if (rc) break;
+      HOST_TRY(cudaMemcpyAsync(c->rot_stage + o * 9, rotation_body_host + o * 9, (size_t)nb * 9 * sizeof(float),
                                 cudaMemcpyHostToDevice, st));
       drot = c->rot_stage + o * 9;
       dw = c->wrench_stage + o * 12;
@@ -496,13 +537,14 @@ int srbd_mpc_solve_host(srbd_ctx* c, const double* const* in17_host, const float
                      nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st);
     if (rc) break;
     if (!zero_copy)
-      SRBD_CUDA(cudaMemcpyAsync(wrench_host + o * 12, c->wrench_stage + o * 12, (size_t)nb * 12 * sizeof(float),
+      HOST_TRY(cudaMemcpyAsync(wrench_host + o * 12, c->wrench_stage + o * 12, (size_t)nb * 12 * sizeof(float),
                                 cudaMemcpyDeviceToHost, st));
-    if (x_out_host) SRBD_CUDA(cudaMemcpyAsync(x_out_host + o * NZ, c->it[0] + o * NZ, (size_t)nb * NZ * sizeof(double),
+    if (x_out_host) HOST_TRY(cudaMemcpyAsync(x_out_host + o * NZ, c->it[0] + o * NZ, (size_t)nb * NZ * sizeof(double),
                                               cudaMemcpyDeviceToHost, st));
-    if (res_out_host) SRBD_CUDA(cudaMemcpyAsync(res_out_host + o * 4, c->res + o * 4, (size_t)nb * 4 * sizeof(double),
+    if (res_out_host) HOST_TRY(cudaMemcpyAsync(res_out_host + o * 4, c->res + o * 4, (size_t)nb * 4 * sizeof(double),
                                                 cudaMemcpyDeviceToHost, st));
   }
+#undef HOST_TRY
   cudaError_t e1 = cudaStreamSynchronize(c->stream);
   cudaError_t e2 = cudaStreamSynchronize(c->stream2);
   if (rc) return rc;
@@ -514,20 +556,26 @@ int srbd_mpc_solve_host(srbd_ctx* c, const double* const* in17_host, const float
 }  // extern "C"
 
 // ---- CusADi-compatible shims ----------------------------------------------------------------
+// `inputs` / `outputs` are DEVICE arrays of device pointers (CusadiFunction.py:84-92): both tables are fetched with
+// two asynchronous copies into the per-device pinned area and one stream synchronisation.  Nothing is allocated per
+// call: the PDIPM scratch lives in the per-device CompatWs and only grows when a larger batch arrives.
 namespace {
-double* g_compat_work = nullptr;
-size_t g_compat_work_B = 0;
 template <int NIN, int NOUT, class F>
 float compat_eval(const double** inputs, double** outputs, int B, F&& launch) {
   if (!inputs || !outputs || B < 0) return -1.f;
-  const double* hin[NIN];
-  double* hout[NOUT];
-  if (cudaMemcpy(hin, inputs, sizeof(hin), cudaMemcpyDeviceToHost) != cudaSuccess) return -2.f;
-  if (cudaMemcpy(hout, outputs, sizeof(hout), cudaMemcpyDeviceToHost) != cudaSuccess) return -2.f;
+  if (ensure_init()) return -2.f;
+  CompatWs* ws = compat_ws();
+  if (!ws) return -3.f;
+  std::lock_guard<std::mutex> lk(ws->mu);
+  const double** hin = (const double**)(ws->host + 1);
+  double** hout = (double**)(ws->host + 1 + NIN);
+  if (cudaMemcpyAsync(hin, inputs, NIN * sizeof(void*), cudaMemcpyDeviceToHost, 0) != cudaSuccess) return -2.f;
+  if (cudaMemcpyAsync(hout, outputs, NOUT * sizeof(void*), cudaMemcpyDeviceToHost, 0) != cudaSuccess) return -2.f;
+  if (cudaStreamSynchronize(0) != cudaSuccess) return -2.f;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, 0);
-  const int rc = launch(hin, hout);
+  const int rc = launch(ws, hin, hout);
   cudaEventRecord(e1, 0);
   cudaEventSynchronize(e1);
   float ms = 0.f;
@@ -536,31 +584,73 @@ float compat_eval(const double** inputs, double** outputs, int B, F&& launch) {
   if (rc) return (float)rc;
   return ms / 1000.f;
 }
+int compat_grow_work(CompatWs* ws, size_t doubles) {
+  if (doubles <= ws->work_doubles) return SRBD_OK;
+  cudaFree(ws->work);
+  ws->work = nullptr; ws->work_doubles = 0;
+  if (cudaMalloc((void**)&ws->work, doubles * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return SRBD_ENOMEM; }
+  ws->work_doubles = doubles;
+  return SRBD_OK;
+}
 }  // namespace
 
 extern "C" {
 
 float srbd_qp_former_evaluate(const double** inputs, double* /*work*/, double** outputs, int batch_size) {
-  return compat_eval<QP_N_IN, QP_N_OUT>(inputs, outputs, batch_size, [&](const double** hin, double** hout) {
+  return compat_eval<QP_N_IN, QP_N_OUT>(inputs, outputs, batch_size, [&](CompatWs*, const double** hin, double** hout) {
     return srbd_qp_form(hin, hout, batch_size, nullptr);
   });
 }
 
 float srbd_sparse_pdipm_multiple_iterations_evaluate(const double** inputs, double* /*work*/, double** outputs,
                                                       int batch_size) {
-  if ((size_t)batch_size > g_compat_work_B) {
-    cudaFree(g_compat_work);
-    g_compat_work = nullptr; g_compat_work_B = 0;
-    if (cudaMalloc((void**)&g_compat_work, srbd_pdipm_work_doubles(batch_size) * sizeof(double)) != cudaSuccess) return -3.f;
-    g_compat_work_B = (size_t)batch_size;
-  }
-  return compat_eval<IP_N_IN, IP_N_OUT>(inputs, outputs, batch_size, [&](const double** hin, double** hout) {
-    // arbitrary values on the frozen pattern are accepted; the call is synchronous by contract, so
-    // the data is probed first and qp_former-shaped batches take the fast kernel
-    int inv = 0;
-    int rc = srbd_pdipm_is_stage_invariant(hin, batch_size, nullptr, &inv);
+  return compat_eval<IP_N_IN, IP_N_OUT>(inputs, outputs, batch_size, [&](CompatWs* ws, const double** hin, double** hout) {
+    // Arbitrary values on the frozen pattern are accepted.  The fast kernel is launched first and verifies per env
+    // that the data is qp_former-shaped (stage-invariant, unit E / Mx coefficients: PdipmArgs::inv_flag); only when
+    // an env fails that check is the batch solved again by the general kernel.  The call is synchronous by contract
+    // (generateCUDACode.py:166-177), so reading the flag back costs no extra synchronisation on the common path.
+    if (batch_size == 0) return (int)SRBD_OK;
+    int rc = compat_grow_work(ws, srbd_pdipm_work_doubles(batch_size, SRBD_STAGE_INVARIANT));
     if (rc) return rc;
-    return srbd_pdipm(hin, hout, g_compat_work, nullptr, batch_size, 5, 0.0, inv ? SRBD_STAGE_INVARIANT : 0u, nullptr);
+    PdipmArgs a;
+    for (int i = 0; i < IP_N_IN; ++i) { if (!hin[i]) return (int)SRBD_EINVAL; a.in[i] = hin[i]; }
+    for (int i = 0; i < IP_N_OUT; ++i) { if (!hout[i]) return (int)SRBD_EINVAL; a.out[i] = hout[i]; }
+    a.work = ws->work; a.work_stride = PDIPM_WORK_DOUBLES_FAST; a.inv_flag = ws->flag;
+    a.iters_done = nullptr; a.num_iters = 5; a.tol = 0.0; a.cold_start = 0;
+    a.fused = 0; a.rot = nullptr; a.wrench = nullptr; a.warm_xy = 0; a.reset = nullptr;
+    for (int i = 0; i < QP_N_IN; ++i) a.qp_in[i] = nullptr;
+    // in10[6..9] may alias out6[0..3]; the fast kernel copies the iterates first, so a rerun needs the originals:
+    // when they alias, the (rare) general-kernel fallback cannot be taken after the fact, so probe up front instead
+    bool alias = false;
+    for (int i = 0; i < 4; ++i) alias |= (hin[IP_X + i] == hout[IPO_X + i]);
+    if (alias) {
+      int inv = 0;
+      cudaError_t e = cudaMemsetAsync(ws->flag, 0, sizeof(int), 0);
+      if (e == cudaSuccess) e = launch_stage_invariant_probe(hin[IP_Q], hin[IP_G], hin[IP_A], ws->flag, batch_size, 0);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(ws->host, ws->flag, sizeof(int), cudaMemcpyDeviceToHost, 0);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+      if (e != cudaSuccess) return cuda_fail(e);
+      inv = (*(volatile int*)ws->host == 0);
+      if (!inv) {
+        rc = compat_grow_work(ws, srbd_pdipm_work_doubles(batch_size, 0));
+        if (rc) return rc;
+        a.work = ws->work; a.work_stride = PDIPM_WORK_DOUBLES;
+      }
+      a.inv_flag = nullptr;
+      SRBD_CUDA(launch_pdipm(a, batch_size, inv != 0, num_sms(), 0));
+      return (int)SRBD_OK;
+    }
+    SRBD_CUDA(cudaMemsetAsync(ws->flag, 0, sizeof(int), 0));
+    SRBD_CUDA(launch_pdipm(a, batch_size, true, num_sms(), 0));
+    SRBD_CUDA(cudaMemcpyAsync(ws->host, ws->flag, sizeof(int), cudaMemcpyDeviceToHost, 0));
+    SRBD_CUDA(cudaStreamSynchronize(0));
+    if (*(volatile int*)ws->host != 0) {   // not qp_former-shaped: the general kernel
+      rc = compat_grow_work(ws, srbd_pdipm_work_doubles(batch_size, 0));
+      if (rc) return rc;
+      a.work = ws->work; a.work_stride = PDIPM_WORK_DOUBLES; a.inv_flag = nullptr;
+      SRBD_CUDA(launch_pdipm(a, batch_size, false, num_sms(), 0));
+    }
+    return (int)SRBD_OK;
   });
 }
 

@@ -14,7 +14,10 @@ struct QpFormArgs {
 struct PdipmArgs {
   const double* in[IP_N_IN];    // Q_val, G_val, A_val, f, h, b, x, s, z, y   (B, nnz) each
   double* out[IP_N_OUT];        // x, s, z, y, residuals(4), mu(1)
-  double* work;                 // (B, PDIPM_WORK_DOUBLES) scratch owned by the caller
+  double* work;                 // (B, work_stride) scratch owned by the caller
+  int work_stride;              // doubles per env: PDIPM_WORK_DOUBLES_FAST (fast kernel) or PDIPM_WORK_DOUBLES
+  int* inv_flag;                // optional (fast kernel, CCS inputs): the kernel verifies that the env's data is
+                                //   stage-invariant (what the synchronous probe checks) and sets *inv_flag = 1 otherwise
   int* iters_done;              // optional (B) per-env Newton iterations executed
   int num_iters;                // Newton iterations per call (runtime, reference bakes 5)
   double tol;                   // <= 0: fixed iteration count; > 0: stop when rx,rs,re,mu < tol
@@ -31,7 +34,8 @@ struct PdipmArgs {
   const float* rot;             // optional (B,3,3) fp32 row-major state-estimate rotation
   float* wrench;                // optional (B,2,6) fp32 (mpc_controller_cusadi.py:186-203)
 };
-constexpr int PDIPM_WORK_DOUBLES = 6224;  // per env: directions + per-row barrier data (1 344) and, for the general
-                                          // kernel, the ten stage buffers prepared once per call (10 x 488)
+constexpr int PDIPM_WORK_DOUBLES = 6224;  // general kernel, per env: directions + per-row barrier data (1 344) and the ten
+                                          // stage buffers prepared once per call (10 x 488)
+constexpr int PDIPM_WORK_DOUBLES_FAST = 1024;   // fast kernel (SRBD_STAGE_INVARIANT, fused tick): srbd_pdipm_fast.h FW_END
 
 }  // namespace srbd

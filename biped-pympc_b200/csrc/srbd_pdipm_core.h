@@ -655,7 +655,7 @@ struct PdipmWarp {
     gF = A.in[IP_F] + e * NZ; gH = A.in[IP_H] + e * NINEQ; gB = A.in[IP_B] + e * NEQ;
     oX = A.out[IPO_X] + e * NZ; oS = A.out[IPO_S] + e * NINEQ; oZ = A.out[IPO_Z] + e * NINEQ;
     oY = A.out[IPO_Y] + e * NEQ; oRes = A.out[IPO_RES] + e * 4; oMu = A.out[IPO_MU] + e;
-    ws = A.work + e * (long long)PDIPM_WORK_DOUBLES;
+    ws = A.work + e * (long long)A.work_stride;
 
     // ---- initial iterate -> output buffers (updated in place from here on) ---------------
     if (A.cold_start) {

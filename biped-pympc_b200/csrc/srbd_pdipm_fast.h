@@ -59,7 +59,7 @@ struct FastSmem {
 enum : int { FW_DX = 0, FW_DY = 240, FW_S = 380, FW_Z = 540, FW_Q = 700,
              // fused tick only: f of the states, c_d | c_d + A_d x0, F_max * contact
              FW_FX = 860, FW_CD = 980, FW_FC = 1004, FW_END = 1024 };
-static_assert(FW_END <= PDIPM_WORK_DOUBLES, "work buffer too small");
+static_assert(FW_END <= PDIPM_WORK_DOUBLES_FAST, "work buffer too small");
 
 // host: gather table of the fast path from the table of srbd_stage_table.h
 inline void build_fast_slots(const StageSlot* sb, StageSlot* fs) {
@@ -109,7 +109,7 @@ struct PdipmFast {
 
   SRBD_DEV const double* gin(int i, int nnz) const { return pa->in[i] + e * nnz; }
   SRBD_DEV double* gout(int i, int nnz) const { return pa->out[i] + e * nnz; }
-  SRBD_DEV double* gws() const { return pa->work + e * (long long)PDIPM_WORK_DOUBLES; }
+  SRBD_DEV double* gws() const { return pa->work + e * (long long)pa->work_stride; }
 
   SRBD_DEV double* P(int k) const { return sm + SM::OFF_P + 78 * k; }
   SRBD_DEV double* fb() const { return sm + SM::OFF_FB; }
@@ -142,7 +142,18 @@ struct PdipmFast {
       if (i < FB_RAW) f[i] = v;
       else if (v != 1.0) bad = 1;
     }
+    if (pa->inv_flag) {   // the probe of srbd_misc.cu folded into the call: every stage carries the values of stage 1
+      int diff = 0;
+      for (int i = lane; i < 36 * 8; i += 32) diff |= (ldg(gA + 36 + i) != ldg(gA + i % 36));
+      for (int c = lane; c < 12; c += 32) diff |= (ldg(gA + 324 + c) != 1.0) | (ldg(gA + a_xcol_off(c)) != 1.0);
+      for (int i = lane; i < 86 * 9; i += 32) diff |= (ldg(gA + 336 + 86 + i) != ldg(gA + 336 + i % 86));
+      if (lane < 2) diff |= (ldg(gA + 336 + a_ucol_off(6 + 3 * lane) + A_UCOL_MX_POS) != 1.0);
+      for (int i = lane; i < 28 * 9; i += 32) diff |= (ldg(gG + 28 + i) != ldg(gG + i % 28));
+      for (int i = lane; i < 108; i += 32) diff |= (ldg(gQ + 12 + i) != ldg(gQ + i % 12)) | (ldg(gQ + 132 + i) != ldg(gQ + 120 + i % 12));
+      if (diff) bad = 1;
+    }
     for (int m = 16; m >= 1; m >>= 1) bad |= w.shfl_i(bad, lane ^ m);
+    if (bad && pa->inv_flag && lane == 0) *pa->inv_flag = 1;
     w.sync();
     }
     const int q = rr;

@@ -13,6 +13,8 @@
 //     host from srbd_pattern.h) encodes the frozen CCS patterns.  No scratch `work`
 //     array, no pre-zeroed outputs: every output element is written.
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 
 #include "srbd_kernels.h"
@@ -159,13 +161,17 @@ cudaError_t launch_qp_form(const QpFormArgs& args, int B, int num_sms, cudaStrea
   // memory allow 10 per SM on sm_100a): a larger grid leaves a second, nearly empty wave that runs its tiles
   // at a fifth of the occupancy (ncu with 12 per SM: 1.20 waves, 4.3 TB/s at 65 536 envs; 5.4 TB/s with 10).  One
   // tile per CTA (hardware scheduling) measures the same to 3 %.
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
+  // (a property of the kernel image and the architecture, identical on every sm_100a device; the cached value is an
+  //  atomic so that concurrent first calls from several host threads are benign)
+  static std::atomic<int> ctas_per_sm{0};
+  int cps = ctas_per_sm.load(std::memory_order_relaxed);
+  if (cps == 0) {
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, qp_form_kernel<kEnvs>, 32 * kEnvs, 0) != cudaSuccess || n < 1) n = 8;
-    ctas_per_sm = n;
+    ctas_per_sm.store(n, std::memory_order_relaxed);
+    cps = n;
   }
-  const int max_ctas = num_sms * ctas_per_sm;
+  const int max_ctas = num_sms * cps;
   const int grid = tiles < max_ctas ? tiles : max_ctas;
   qp_form_kernel<kEnvs><<<grid, 32 * kEnvs, 0, stream>>>(args, B);
   return cudaGetLastError();

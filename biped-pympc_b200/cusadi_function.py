@@ -78,10 +78,16 @@ class B200Function:
     def __init__(self, fn, num_instances: int, device="cuda", num_iters: int = 5, tol: float = 0.0,
                  stage_invariant=None):
         import torch
-        if isinstance(fn, str):
-            fn = {"qp_former": QP_FORMER_FUNCTION, "sparse_pdipm_multiple_iterations": PDIPM_FUNCTION}[fn]
-        if fn.name() not in ("qp_former", "sparse_pdipm_multiple_iterations"):
-            raise ValueError(f"no B200 kernel for function {fn.name()!r}")
+        # `fn` may be the function's name or any object with a .name() -- in particular the casadi.Function the reference
+        # passes to CusadiFunction (mpc_controller_cusadi.py:28-34).  Either way the metadata comes from the library's own
+        # frozen patterns (FunctionSpec): a casadi.Function has no triplet_out(), and the kernels are tied to these
+        # patterns anyway.  The caller's object is kept for reference only.
+        name = fn if isinstance(fn, str) else fn.name()
+        specs = {"qp_former": QP_FORMER_FUNCTION, "sparse_pdipm_multiple_iterations": PDIPM_FUNCTION}
+        if name not in specs:
+            raise ValueError(f"no B200 kernel for function {name!r}")
+        self.fn_casadi_given = None if isinstance(fn, str) else fn
+        fn = specs[name]
         _native.load()                      # fail loudly if the CUDA library is missing
         if not torch.cuda.is_available():
             raise _native.SrbdError("B200Function needs a CUDA device (there is no CPU fallback)")
@@ -98,7 +104,10 @@ class B200Function:
         self._input_tensors: List = [None] * fn.n_in()
         self._output_tensors = [torch.empty((B, fn.nnz_out(i)), dtype=torch.float64, device=self._device)
                                 for i in range(fn.n_out())]
-        self._work = (torch.empty((B, _native.WORK_DOUBLES), dtype=torch.float64, device=self._device)
+        # scratch for either kernel (the general one needs the larger buffer); stage_invariant=True callers only need
+        # WORK_DOUBLES_FAST per env
+        per_env = _native.WORK_DOUBLES_FAST if stage_invariant is True else _native.WORK_DOUBLES
+        self._work = (torch.empty((B, per_env), dtype=torch.float64, device=self._device)
                       if self.fn_name != "qp_former" else None)
         self.iters_done = (torch.zeros(B, dtype=torch.int32, device=self._device)
                            if self.fn_name != "qp_former" else None)
@@ -109,6 +118,12 @@ class B200Function:
     def evaluate(self, inputs: Sequence):
         if len(inputs) != self.fn_casadi.n_in():
             raise ValueError(f"{self.fn_name}: expected {self.fn_casadi.n_in()} inputs, got {len(inputs)}")
+        # the reference's operator has a fixed batch: its buffers are allocated for num_instances envs and the generated
+        # kernel is launched with num_instances threads (CusadiFunction.py:43-46); a different batch is an error here
+        for i, t in enumerate(inputs):
+            if t is not None and t.numel() != self.num_instances * self.fn_casadi.nnz_in(i):
+                raise ValueError(f"{self.fn_name}: input {i} has {t.numel()} elements, expected "
+                                 f"{self.num_instances} x {self.fn_casadi.nnz_in(i)} (num_instances is fixed at construction)")
         self._input_tensors = list(inputs)
         self.inputs_sparse = self._input_tensors
         if self.fn_name == "qp_former":

@@ -10,12 +10,15 @@ base_controller.py:61-257; ``x0 / x_ref / R_body`` are built on the device by ``
 key in its solver switch (biped_controller.py:36-45).  It is written as a mixin-style class
 with no dependency on the reference package (which cannot be imported without CasADi).
 
-Marshalling follows mpc_controller_cusadi.py:54-95 including its flattening quirks
+Marshalling follows mpc_controller_cusadi.py:54-95 including its three layout quirks
 (SURVEY.md 8b): ``R_body`` and the ``(B,10,2)`` contact table are flattened row-major into
-buffers the kernel reads in CasADi column-major order (Q1, Q2).  ``fix_layout=True`` passes
-the mathematically intended layout instead.  Q3 (13-long ``Q`` strided by 12) is *not*
-reproduced by default: ``Q[:12]`` is used for every env; ``reproduce_q_stride_bug=True``
-restores the reference's behaviour bit for bit.
+buffers the kernel reads in CasADi column-major order (Q1, Q2), and the 13-long ``MPCConf.Q``
+is strided by 12 so that env e reads ``Qflat[12e : 12e+12]`` (Q3).  ONE switch governs all
+three: ``reference_quirks = True`` (the default) reproduces the reference's ``run()`` bit for
+bit, ``reference_quirks = False`` passes the mathematically intended layouts and ``Q[:12]``
+for every env.  ``fix_layout`` / ``reproduce_q_stride_bug`` override the individual quirks
+(``None`` = follow ``reference_quirks``); an incoherent combination with a ``Q`` that is not
+12 long warns once.
 """
 from __future__ import annotations
 
@@ -102,9 +105,22 @@ class MPCControllerB200:
 
     MAX_ITER = 4          # calls per tick, mpc_controller_cusadi.py:144
     ITERS_PER_CALL = 5    # generate_solver_function.py:106
-    fix_layout = False
-    reproduce_q_stride_bug = False
+    reference_quirks = True          # Q1-Q3 as the reference has them: run() == MPCControllerCusadi.run()
+    fix_layout = None                # override of Q1 / Q2 (None = not reference_quirks)
+    reproduce_q_stride_bug = None    # override of Q3      (None = reference_quirks)
     tol = 0.0
+    _warned_quirks = False
+
+    def _quirk_flags(self):
+        fix = (not self.reference_quirks) if self.fix_layout is None else bool(self.fix_layout)
+        qbug = self.reference_quirks if self.reproduce_q_stride_bug is None else bool(self.reproduce_q_stride_bug)
+        if not fix and not qbug and self.Q.numel() != 12 and not MPCControllerB200._warned_quirks:
+            import warnings
+            warnings.warn("MPCControllerB200: the reference's R_body / contact-table flattening is reproduced but its "
+                          f"stride-12 read of the {self.Q.numel()}-long Q is not: the wrench differs from "
+                          "MPCControllerCusadi.run() for every env after env 0 (set reference_quirks or both overrides)")
+            MPCControllerB200._warned_quirks = True
+        return fix, qbug
 
     def init_solver(self):
         _native.load()
@@ -166,7 +182,8 @@ class MPCControllerB200:
                 fn = getattr(self, hook, None)
                 if fn is not None:
                     fn()
-        inputs = marshal_inputs(self, self.fix_layout, self.reproduce_q_stride_bug, with_linearisation_point=False)
+        fix, qbug = self._quirk_flags()
+        inputs = marshal_inputs(self, fix, qbug, with_linearisation_point=False)
         foot_wrench = self._ctx.solve(inputs, self.state_estimate_data.rotation_body,
                                       self.MAX_ITER, self.ITERS_PER_CALL, self.tol)
         cost = torch.zeros(self.num_envs, device=self.device)   # reference hard-wires 0 (:185)

@@ -25,8 +25,20 @@
  *
  * All functions return 0 on success or a negative SRBD_E* code; none of them calls exit().
  * Kernels are launched asynchronously on the caller's stream (a cudaStream_t passed as
- * void*; NULL = legacy default stream) unless stated otherwise.  The functions are
- * re-entrant given distinct buffers; call srbd_init() once per device first.
+ * void*; NULL = legacy default stream) unless stated otherwise.
+ *
+ * Threading.  The native entry points (srbd_qp_form, srbd_pdipm, srbd_marshal_inputs, srbd_wrench,
+ * srbd_gait, srbd_reference_trajectory, srbd_update_state, srbd_lowlevel, srbd_t1_kinematics) keep no
+ * state between calls beyond per-device one-time configuration, which is guarded (mutex / atomics):
+ * they may be called concurrently from several host threads and on several devices given distinct
+ * buffers.  A srbd_ctx owns buffers and two internal streams and serves ONE caller (one stream) at a
+ * time.  The synchronous entries -- srbd_pdipm_is_stage_invariant and the two CusADi-compatible
+ * `evaluate` functions -- share a per-device scratch area behind a per-device mutex: concurrent
+ * callers on one device are serialised, callers on different devices are not.
+ *
+ * Alignment.  srbd_qp_form moves x, u, x_ref and its six outputs as 16-byte vectors: those pointers
+ * must be 16-byte aligned (any cudaMalloc / torch allocation is; a view at an odd double offset is
+ * not) -- SRBD_EINVAL otherwise.  Everything else only needs natural (8-byte) alignment.
  */
 #ifndef SRBD_MPC_H_
 #define SRBD_MPC_H_
@@ -84,8 +96,10 @@ int srbd_pattern(char which /* 'H','A','G' */, const int** colptr, const int** r
 /* replaces libqp_former.so::evaluate (generateCUDACode.py:160-183) */
 int srbd_qp_form(const double* const* in17, double* const* out6, int B, void* stream);
 
-/* scratch doubles the caller must provide to srbd_pdipm for B environments */
-size_t srbd_pdipm_work_doubles(int B);
+/* scratch doubles the caller must provide to srbd_pdipm for B environments when it is called with
+ * `flags`: 1 024 per env with SRBD_STAGE_INVARIANT (the fast kernel), 6 224 per env without (the general
+ * kernel parks its ten prepared stage buffers there). */
+size_t srbd_pdipm_work_doubles(int B, unsigned flags);
 
 /* replaces libsparse_pdipm_multiple_iterations.so::evaluate; the iteration count is a
  * runtime argument (the reference bakes num_iters=5, generate_solver_function.py:106).
@@ -237,12 +251,14 @@ int srbd_mpc_solve_host(srbd_ctx* ctx, const double* const* in17_host, const flo
 
 /* ---- CusADi-compatible entry points (drop-in for CusadiFunction.py:43) ---------------- *
  * Same signature and pointer convention as the generated `evaluate`: `inputs`/`outputs`  *
- * are DEVICE arrays of device pointers, `work` is ignored (the kernels keep their        *
- * scratch in shared memory / an internal buffer), the call runs on the legacy default    *
- * stream, is synchronous and returns the kernel time in seconds (negative on error).     *
- * The PDIPM variant performs the reference's fixed 5 Newton iterations; it probes the    *
- * batch (srbd_pdipm_is_stage_invariant) and takes the fast kernel for qp_former-shaped   *
- * data, the general kernel for arbitrary values on the frozen pattern.                   */
+ * are DEVICE arrays of device pointers, `work` is ignored (its size is not part of the   *
+ * signature; the kernels keep their scratch in shared memory and in a per-device buffer  *
+ * that only grows when a larger batch arrives -- nothing is allocated per call), the     *
+ * call runs on the legacy default stream, is synchronous and returns the kernel time in  *
+ * seconds (negative on error).  The PDIPM variant performs the reference's fixed 5       *
+ * Newton iterations with the fast kernel, which verifies per env that the data is        *
+ * qp_former-shaped; if an env is not, the batch is solved again by the general kernel    *
+ * (arbitrary values on the frozen pattern).                                              */
 float srbd_qp_former_evaluate(const double** inputs, double* work, double** outputs, int batch_size);
 float srbd_sparse_pdipm_multiple_iterations_evaluate(const double** inputs, double* work, double** outputs,
                                                       int batch_size);

@@ -156,7 +156,10 @@ class StackRollout:
 
 def main(B=4096, steps=1000, decimation=10, mpc_calls=4, iters_per_call=5, warmup=20, dev="cuda:0", seed=1, graphs=0):
     import biped_pympc_b200 as bp
-    c = bp.BipedControllerB200(B, dev, decimation=decimation, mpc_calls=mpc_calls, mpc_iters_per_call=iters_per_call)
+    # a 12-long Q: the first 12 entries of MPCConf.Q (configuration.py:43-47) for every env, so that the reference's stride-12
+    # read of its 13-long Q plays no role in the rollout
+    c = bp.BipedControllerB200(B, dev, decimation=decimation, mpc_calls=mpc_calls, mpc_iters_per_call=iters_per_call,
+                               Q=[150, 150, 250, 100, 100, 250, 1, 1, 5, 10, 10, 1])
     if graphs:
         c.capture_graphs()
     ro = StackRollout(c, seed=seed, graphs=bool(graphs))

@@ -10,7 +10,6 @@
 
 #include "srbd_stage_table.h"
 #include "srbd_pdipm_fast.h"
-#include "srbd_pdipm_pair.h"
 
 namespace srbd {
 static std::map<std::string, std::vector<double>> g_trace;
@@ -49,22 +48,6 @@ static void run_env_fast(const PdipmArgs& A, long long e, const StageSlot* slots
   });
 }
 
-// two environments per emulated warp (srbd_pdipm_pair.h): envs e0 and e0 + 1 (the second may not exist)
-static void run_env_pair(const PdipmArgs& A, long long e0, int B, const StageSlot* slots) {
-  std::vector<double> smem(2 * FastSmem::SIZE, 0.0);
-  run_warp([&](int lane) {
-    PdipmPair W;
-    W.w.lane_ = lane;
-    const int slot = lane >> 4;
-    long long e = e0 + slot;
-    const bool exists = e < B;
-    if (!exists) e = B - 1;
-    W.sm = smem.data() + slot * FastSmem::SIZE;
-    W.slots = slots;
-    W.run(A, e, exists);
-  }, 1 << 21);
-}
-
 extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, double* work, int* iters_done,
                                int B, int num_iters, double tol, int cold_start, int uniform, int trace) {
   static StageSlot slots[SB_SIZE];
@@ -74,14 +57,13 @@ extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, d
   PdipmArgs A;
   for (int i = 0; i < IP_N_IN; ++i) A.in[i] = in10[i];
   for (int i = 0; i < IP_N_OUT; ++i) A.out[i] = out6[i];
-  A.work = work; A.iters_done = iters_done; A.num_iters = num_iters; A.tol = tol; A.cold_start = cold_start;
+  A.work = work; A.work_stride = PDIPM_WORK_DOUBLES; A.inv_flag = nullptr; A.iters_done = iters_done; A.num_iters = num_iters; A.tol = tol; A.cold_start = cold_start;
   A.fused = 0; A.rot = nullptr; A.wrench = nullptr; A.warm_xy = 0; A.reset = nullptr;
   for (int i = 0; i < QP_N_IN; ++i) A.qp_in[i] = nullptr;
   g_trace_on = trace != 0;
   g_trace.clear();
   for (long long e = 0; e < B; ++e) {
-    if (uniform == 3) { if ((e & 1) == 0) run_env_pair(A, e, B, fslots); }
-    else if (uniform == 2) run_env_fast(A, e, fslots);
+    if (uniform == 2) run_env_fast(A, e, fslots);
     else if (uniform) run_env<true>(A, e, slots, nullptr);
     else run_env<false>(A, e, slots, nullptr);
   }
@@ -100,11 +82,11 @@ extern "C" int srbd_emul_tick(const double* const* in17, const float* rot, doubl
   for (int i = 0; i < IP_N_IN; ++i) A.in[i] = nullptr;
   for (int i = 0; i < QP_N_IN; ++i) A.qp_in[i] = in17[i];
   for (int i = 0; i < IP_N_OUT; ++i) A.out[i] = out6[i];
-  A.work = work; A.iters_done = iters_done; A.num_iters = num_iters; A.tol = tol; A.cold_start = 1;
+  A.work = work; A.work_stride = PDIPM_WORK_DOUBLES; A.inv_flag = nullptr; A.iters_done = iters_done; A.num_iters = num_iters; A.tol = tol; A.cold_start = 1;
   A.fused = 1; A.rot = rot; A.wrench = wrench; A.warm_xy = warm; A.reset = reset;
   g_trace_on = false;
-  if (pair) { for (long long e = 0; e < B; e += 2) run_env_pair(A, e, B, fslots); }
-  else { for (long long e = 0; e < B; ++e) run_env_fast(A, e, fslots); }
+  (void)pair;
+  for (long long e = 0; e < B; ++e) run_env_fast(A, e, fslots);
   return 0;
 }
 

@@ -72,7 +72,6 @@ def emul_pdipm(qp, iters, x=None, s=None, z=None, y=None, tol=0.0, uniform=True,
     """Runs the PDIPM *device code* under the CPU warp emulator.  Returns (outs6, iters_done).
     uniform: False = general kernel (srbd_pdipm_core.h, arbitrary values on the pattern),
              True / 2 = stage-invariant fast kernel (srbd_pdipm_fast.h),
-             3 = the same mathematics with two environments per warp (srbd_pdipm_pair.h),
              1 = stage-invariant instantiation of the general kernel."""
     if uniform is True:
         uniform = 2

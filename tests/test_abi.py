@@ -43,7 +43,8 @@ def test_nnz_tables():
     assert [lib.srbd_pdipm_nnz_in(i) for i in range(10)] == list(so.PDIPM_NNZ_IN)
     assert [lib.srbd_pdipm_nnz_out(i) for i in range(6)] == list(so.PDIPM_NNZ_OUT)
     assert lib.srbd_qp_former_nnz_in(17) < 0 and lib.srbd_pdipm_nnz_out(-1) < 0
-    assert lib.srbd_pdipm_work_doubles(3) == 3 * bp._native.WORK_DOUBLES
+    assert lib.srbd_pdipm_work_doubles(3, 0) == 3 * bp._native.WORK_DOUBLES
+    assert lib.srbd_pdipm_work_doubles(3, bp._native.STAGE_INVARIANT) == 3 * bp._native.WORK_DOUBLES_FAST == 3 * 1024
 
 
 def test_patterns_match_oracle_structure():
@@ -74,6 +75,11 @@ def test_error_paths_do_not_exit():
     assert lib.srbd_gait(None, None, None, None, 0.001, 1, 10, None, None, None, None, 4, None) == -1
     assert lib.srbd_update_state(None, None, 43, 4, None) == -1
     assert lib.srbd_lowlevel(None, None, None, None, 0.001, 0, 1, 4, None) == -1
+    # alignment contract of srbd_qp_form (16-byte vectors): checked before anything touches the device
+    PP = ctypes.c_void_p * 17
+    ins = PP(*[0x1000 + 0x100 * i for i in range(17)]); outs = (ctypes.c_void_p * 6)(*[0x9000 + 0x100 * i for i in range(6)])
+    ins[3] = 0x1308                                       # x_ref at an odd double offset
+    assert lib.srbd_qp_form(ins, outs, 4, None) == -1
     empty = bp.biped_controller._LoopBuffers()          # all-null buffers are rejected, not dereferenced
     assert lib.srbd_update_state(ctypes.byref(empty), None, 43, 4, None) == -1
 

@@ -109,26 +109,6 @@ def test_fused_tick_equals_assembly_then_solve():
         assert np.abs(w[e] - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
 
 
-def test_two_envs_per_warp_mapping_matches_one_env_per_warp(qp_small):
-    """srbd_pdipm_pair.h (experimental mapping, SRBD_PDIPM_PAIR=1): same arithmetic per matrix row, so
-    the affine direction is bit-identical; only the order of the mu / residual reductions differs,
-    which enters the corrector through sigma * mu (last-bit differences in the first iterate).  Odd batch sizes exercise the read-only shadow
-    slot of the last warp."""
-    qp3 = [t[:3] for t in qp_small]
-    a, ia = emul_pdipm(qp3, 1, uniform=2)
-    b, ib = emul_pdipm(qp3, 1, uniform=3)
-    for i in range(4):
-        assert rel_err(b[i], a[i]) < 1e-12
-    assert rel_err(b[4], a[4]) < 1e-14 and list(ia) == list(ib)
-    a5, _ = emul_pdipm(qp3, 5, uniform=2)
-    b5, _ = emul_pdipm(qp3, 5, uniform=3)
-    for i in range(4):
-        assert rel_err(b5[i], a5[i]) < 1e-9
-    c5, _ = emul_pdipm(qp3, 5, uniform=3, lane_order=-1)
-    for u, v in zip(b5, c5):
-        assert np.array_equal(u, v)
-
-
 def test_warm_start_semantics():
     """warm_xy keeps (x, y) of the output buffers and re-initialises s = max(h - G x, 1), z = 1; envs
     flagged in `reset` are cold-started (bit-identical to the cold tick)."""

@@ -378,6 +378,72 @@ def test_fast_path_rejects_data_that_is_not_qp_former_shaped(golden):
     assert torch.isfinite(gen[0]).all()
 
 
+def test_compat_evaluate_falls_back_to_the_general_kernel_without_allocating(golden):
+    """The drop-in `evaluate` launches the fast kernel, which verifies per env that the data is qp_former-shaped
+    (PdipmArgs::inv_flag); a batch that is not goes to the general kernel in the same call.  The per-device scratch
+    only grows: a second call of the same size allocates nothing (device memory in use is unchanged)."""
+    import os
+    qp = [golden[f"qp_{n}"] for n in "HfAbGd"]
+    Hv, f, Av, b, Gv, d = _dev(qp)
+    B = Hv.shape[0]
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(bp._native.LIB_PATH), "libsparse_pdipm_multiple_iterations.so"))
+    lib.evaluate.restype = ctypes.c_float
+    lib.evaluate.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    x = torch.zeros(B, 240, dtype=torch.float64, device=DEV)
+    s = torch.maximum(d, torch.ones_like(d)); z = torch.ones_like(d); y = torch.ones(B, 140, dtype=torch.float64, device=DEV)
+
+    def call(Avv):
+        ins = [Hv, Gv, Avv, f, d, b, x, s, z, y]
+        outs = [torch.zeros((B, n), dtype=torch.float64, device=DEV) for n in bp._native.IP_NNZ_OUT]
+        ip = torch.tensor([t.data_ptr() for t in ins], dtype=torch.int64, device=DEV)
+        op = torch.tensor([t.data_ptr() for t in outs], dtype=torch.int64, device=DEV)
+        torch.cuda.synchronize()
+        assert lib.evaluate(ip.data_ptr(), None, op.data_ptr(), B) >= 0
+        return outs
+
+    fast = call(Av)
+    ref = bp.pdipm([Hv, Gv, Av, f, d, b, x, s, z, y], num_iters=5, stage_invariant=True)
+    assert torch.equal(fast[0], ref[0])
+    Av2 = Av.clone(); Av2[1, 36 + 40] *= 1.0 + 1e-6          # stage 2 differs from stage 1 in one env
+    slow = call(Av2)
+    gen = bp.pdipm([Hv, Gv, Av2, f, d, b, x, s, z, y], num_iters=5, stage_invariant=False)
+    assert torch.isfinite(slow[0]).all() and torch.equal(slow[0], gen[0])
+    free0 = torch.cuda.mem_get_info()[0]
+    call(Av); call(Av2)
+    assert torch.cuda.mem_get_info()[0] == free0
+
+
+def test_operator_accepts_a_casadi_like_function_and_checks_its_buffers(golden):
+    """B200Function(fn, B) with the object the reference passes (a casadi.Function: has name(), no triplet_out) resolves
+    to the library's own patterns; a batch other than num_instances and short caller-provided buffers raise."""
+    class FakeCasadiFunction:               # the slice of casadi.Function that identifies the function
+        def name(self): return "qp_former"
+    inputs = _dev([golden[f"in_{n}"] for n in bp.workload.INPUT_NAMES])
+    B = inputs[0].shape[0]
+    fn = bp.B200Function(FakeCasadiFunction(), B)
+    fn.evaluate(inputs)
+    assert tuple(fn.getDenseOutput(0).shape) == (B, 240, 240) and tuple(fn.getDenseOutput(2).shape) == (B, 140, 240)
+    with pytest.raises(ValueError):
+        bp.B200Function("qp_former", B - 1).evaluate(inputs)
+    with pytest.raises(ValueError):
+        bp.qp_form(inputs, out=[torch.empty((B - 1, n), dtype=torch.float64, device=DEV) for n in bp._native.QP_NNZ_OUT])
+    Hv, f, Av, b, Gv, d = bp.qp_form(inputs)
+    with pytest.raises(ValueError):
+        bp.pdipm([Hv, Gv, Av, f, d, b], cold_start=True, stage_invariant=True,
+                 work=torch.empty((B, 100), dtype=torch.float64, device=DEV))
+    with pytest.raises(ValueError):
+        bp.pdipm([Hv, Gv, Av, f, d, b], cold_start=True, stage_invariant=False,
+                 work=torch.empty((B, bp._native.WORK_DOUBLES_FAST), dtype=torch.float64, device=DEV))
+    with pytest.raises((ValueError, TypeError)):
+        bp.pdipm([Hv, Gv, Av, f, d, b], cold_start=True, stage_invariant=True,
+                 iters_done=torch.zeros(B - 1, dtype=torch.int32, device=DEV))
+    # a misaligned view (odd double offset) is refused by the C-ABI instead of faulting in the kernel
+    buf = torch.empty(B * 120 + 1, dtype=torch.float64, device=DEV)
+    bad = list(inputs); bad[3] = buf[1:].view(B, 120); bad[3].copy_(inputs[3])
+    with pytest.raises(bp.SrbdError):
+        bp.qp_form(bad)
+
+
 @pytest.mark.parametrize("B", [1, 13, 14, 15, 29, 2073])
 def test_fused_tick_ragged_batches(B):
     """CTA boundaries of the fused kernel (14 envs per CTA, 148 CTAs per wave): a batch gives the same
