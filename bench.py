@@ -102,31 +102,34 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def cpu_reference_run(n_envs, iters, steps, warmup, threads, seed=20261018):
-    """Times the reference's CPU path on a bounded sample of the workload.  Preferred: oracle/_ref/lib<fn>_cpu.so, the
-    expression tapes of the reference's two functions (built from its sources by oracle/make_cusadi_ref.py) compiled to C
-    and run with `omp parallel for` over envs, the reference's own CPU convention (evaluate_parallel_cpu.cpp:79-82) --
-    kind "reference".  Otherwise the C restatement oracle/srbd_oracle.c (literal qp_former + full-KKT sparse LDL^T
-    PDIPM, OpenMP over envs) -- kind "port".  Returns (solves/s, per-step seconds, kind, description)."""
+def cpu_reference_run(n_envs, iters, steps, warmup, threads, seed=20261018, want="reference"):
+    """Times the reference's CPU path on the workload.  want="reference": oracle/_ref/lib<fn>_cpu*.so, the expression tapes
+    of the reference's two functions (built from its sources by oracle/make_cusadi_ref.py) compiled to C and run with
+    `omp parallel for` over envs, the reference's own CPU convention (evaluate_parallel_cpu.cpp:79-82; gcc -O3
+    -march=native like run_benchmarks.py:46 where the compiler finishes, else the -O1 build) -- kind "reference".
+    want="port" (or no oracle/_ref): the C restatement oracle/srbd_oracle.c (literal qp_former + full-KKT sparse LDL^T
+    PDIPM, gcc -O3 -march=native, OpenMP over envs) -- kind "port".
+    Returns (solves/s, per-step seconds, kind, description)."""
     import biped_pympc_b200 as bp
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import cusadi_ref
     inp, _ = bp.workload.make_batch(n_envs, seed=seed)
-    if cusadi_ref.cpu_available() and iters == 5:
+    if want == "reference" and cusadi_ref.cpu_available() and iters == 5:
         cpu = cusadi_ref.CusadiRefCpu()
 
         def one():
             cpu.pdipm5(cpu.qp_former(inp, threads), threads=threads)
         kind = "reference"
         desc = ("oracle/_ref: expression tapes of the reference's qp_former and sparse_pdipm_multiple_iterations (its sources run over a "
-                "CasADi stand-in; CasADi itself is not installable offline) compiled to C with gcc -O1, omp parallel for over envs")
+                "CasADi stand-in; CasADi itself is not installable offline) compiled to C, omp parallel for over envs; compiler flags: "
+                + cpu.flags)
     else:
         from oracle import c_oracle as co
 
         def one():
             co.pdipm(co.qp_former(inp, nthreads=threads), iters, nthreads=threads)
         kind = "port"
-        desc = "oracle/srbd_oracle.c (port of qp_former + full-KKT sparse LDL^T PDIPM, OpenMP over envs)"
+        desc = "oracle/srbd_oracle.c (port of qp_former + full-KKT sparse LDL^T PDIPM, gcc -O3 -march=native, OpenMP over envs)"
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -138,21 +141,30 @@ def cpu_reference_run(n_envs, iters, steps, warmup, threads, seed=20261018):
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path on the box's host cores, on the metric's own
+    batch (4 096 envs per step, the same seeded workload as the GPU arm), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 2048
-    value, times, kind, desc = cpu_reference_run(sample, ITERS, args.steps, max(args.warmup, 1), threads)
+    B = args.envs
+    # one step is ~0.1-0.2 s of host time: K steps as asked, capped so that the run ends within a few minutes
+    steps = max(1, min(args.steps, 600))
+    value, times, kind, desc = cpu_reference_run(B, ITERS, steps, max(min(args.warmup, 5), 1), threads)
+    port_value, _, _, port_desc = cpu_reference_run(B, ITERS, min(steps, 5), 1, threads, want="port")
     ms = 1e3 * sum(times) / len(times)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{ENVS_PER_GPU}-env batched SRBD MPC, 5 PDIPM iters, fp64 (BASELINE configs[1])",
-                   "envs_per_step_sample": sample, "iters": ITERS, "horizon": 10},
+        "config": {"workload": (f"{B}-env batched SRBD MPC per GPU, 5 PDIPM iters, fp64, cold start "
+                                "(BASELINE configs[1]); form + solve + wrench fused in one kernel via srbd_mpc_solve"),
+                   "envs_per_gpu": B, "iters": ITERS, "horizon": 10, "parallelism": "host threads, omp parallel for over envs",
+                   "steps_timed": steps},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
-                         "sample": f"{sample} envs/step of the same seeded workload; {desc}"},
+                         "sample": f"the metric's full batch: {B} envs/step of the same seeded workload, {steps} steps; {desc}"},
+        "cpu_baseline_port": {"value": port_value, "unit": UNIT, "cores": threads, "kind": "port",
+                              "sample": f"{B} envs/step, {min(steps, 5)} steps; {port_desc}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -220,6 +232,255 @@ def run_cusadi_ref(args, emit=True):
     if emit:
         print(json.dumps(line))
     return line
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Sub-records of the default line: the other BASELINE.json configs, each bounded to a few seconds
+# ----------------------------------------------------------------------------------------------------------------------
+def sub_strong_scaling(bp, torch, dist, dev, local_rank, rank, world, flush, steps=10):
+    """BASELINE configs[2] at fixed total size: 65 536 envs over the N GPUs of the run (65 536 / N per rank), one fused
+    launch per rank, no collective on the solve path; time = max over ranks.  Run by every rank."""
+    total = 65536
+    Bs = total // world
+    inp, rot = bp.workload.make_batch(Bs, seed=20261018 + 1000, rank=rank)
+    ins = [torch.as_tensor(a, device=dev) for a in inp]
+    rot_t = torch.as_tensor(rot, dtype=torch.float32, device=dev)
+    ctx = bp.Context(Bs, local_rank)
+    for _ in range(3):
+        ctx.solve(ins, rot_t, num_calls=1, iters_per_call=ITERS)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.fill_(1.0)
+        a.record()
+        ctx.solve(ins, rot_t, num_calls=1, iters_per_call=ITERS)
+        b.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ctx.close()
+    del ins, rot_t
+    return {"value": total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "envs_total": total, "envs_per_gpu": Bs, "n_gpus": world,
+            "steps": steps, "scaling": "strong", "what": "BASELINE configs[2]: 65 536 envs sharded over the GPUs of this run, 5 PDIPM iterations"}
+
+
+def sub_converge(bp, torch, dev, local_rank, flush, steps=3):
+    """BASELINE configs[3]: 16 384 envs to tol 1e-8 on (|rx|, |rs|, |re|, mu), at most 30 iterations."""
+    B = 16384
+    inp, rot = bp.workload.make_batch(B, seed=20261018 + 2000)
+    ins = [torch.as_tensor(a, device=dev) for a in inp]
+    rot_t = torch.as_tensor(rot, dtype=torch.float32, device=dev)
+    itd = torch.zeros(B, dtype=torch.int32, device=dev)
+    ctx = bp.Context(B, local_rank)
+    ctx.solve(ins, rot_t, num_calls=1, iters_per_call=30, tol=1e-8, iters_done=itd)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.fill_(1.0)
+        a.record()
+        ctx.solve(ins, rot_t, num_calls=1, iters_per_call=30, tol=1e-8, iters_done=itd)
+        b.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    hist = torch.bincount(itd.clamp(min=0).to(torch.int64), minlength=31).tolist()
+    # a looser tolerance for comparison: the iteration counts then differ between envs
+    ctx.solve(ins, rot_t, num_calls=1, iters_per_call=30, tol=1e-2, iters_done=itd)
+    torch.cuda.synchronize()
+    hist2 = torch.bincount(itd.clamp(min=0).to(torch.int64), minlength=31).tolist()
+    ctx.close()
+    return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "envs": B, "max_iters": 30, "tol": 1e-8, "steps": steps,
+            "iterations_histogram": {str(i): c for i, c in enumerate(hist) if c},
+            "iterations_histogram_tol_1e-2": {str(i): c for i, c in enumerate(hist2) if c},
+            "what": "BASELINE configs[3]: run to convergence, beyond the reference's 5-iteration codegen limit"}
+
+
+def sub_closed_loop():
+    """BASELINE configs[4]: gait generator + swing leg + MPC at 4 096 envs for 1 000 control steps (tests/closed_loop_stack.py:
+    BipedControllerB200 in closed loop with a single-rigid-body stand-in plant; only the controller calls are timed)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import closed_loop_stack
+    res = closed_loop_stack.main(B=4096, steps=1000, decimation=10, mpc_calls=4, iters_per_call=5, warmup=20, graphs=1)
+    res["what"] = ("BASELINE configs[4]: 4 096 envs x 1 000 control steps at 1 kHz, MPC tick (4 x 5 iterations) every 10th step, "
+                   "control step replayed as a CUDA graph; latencies in ms per control step")
+    return res
+
+
+class _CompatFunction:
+    """CusadiFunction.py:28-109 restated for measurement: the calling convention an UNMODIFIED CusadiFunction applies to
+    lib<fn>.so::evaluate -- zero-filled outputs and (B, sz_w) work tensor before every call (:104-109), the input
+    pointer table rewritten element by element (:97-102), device arrays of device pointers, and getDenseOutput through
+    torch.sparse_coo_tensor (:49-58).  `libdir` selects whose shared objects are loaded."""
+
+    def __init__(self, spec, B, libdir, sz_w, dev, suffix=""):
+        import ctypes
+        import torch
+        self.fn, self.B, self.dev, self.torch = spec, B, dev, torch
+        self.lib = ctypes.CDLL(os.path.join(libdir, f"lib{spec.name()}{suffix}.so"))
+        self.lib.evaluate.restype = ctypes.c_float
+        self.lib.evaluate.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.outputs_sparse = [torch.zeros(B, spec.nnz_out(i), **f64) for i in range(spec.n_out())]
+        self.work = torch.zeros(B, sz_w, **f64)
+        self.in_ptrs = torch.zeros(spec.n_in(), dtype=torch.int64, device=dev)
+        self.out_ptrs = torch.zeros(spec.n_out(), dtype=torch.int64, device=dev)
+        for i, t in enumerate(self.outputs_sparse):
+            self.out_ptrs[i] = t.data_ptr()
+        self.kernel_s = 0.0
+        self._trip = {i: [self.torch.as_tensor(v) for v in spec.triplet_out(i)] for i in range(spec.n_out())}
+
+    def evaluate(self, inputs):
+        for o in self.outputs_sparse:
+            o.zero_()
+        self.work.zero_()
+        self._keep = [t.contiguous() for t in inputs]
+        for i, t in enumerate(self._keep):
+            self.in_ptrs[i] = t.data_ptr()
+        self.kernel_s += float(self.lib.evaluate(self.in_ptrs.data_ptr(), self.work.data_ptr(), self.out_ptrs.data_ptr(), self.B))
+
+    def getDenseOutput(self, i):
+        torch, fn, B = self.torch, self.fn, self.B
+        nnz = fn.nnz_out(i)
+        env_idx = torch.tensor(range(B), device=self.dev).repeat_interleave(nnz)
+        row_idx = self._trip[i][0].to(self.dev).repeat(B)
+        col_idx = self._trip[i][1].to(self.dev).repeat(B)
+        dim = (B, fn.size1_out(i), fn.size2_out(i))
+        return torch.sparse_coo_tensor(torch.vstack((env_idx, row_idx, col_idx)), self.outputs_sparse[i].reshape(-1), dim).to_dense()
+
+
+def compat_tick(former, solver, inputs, rot, calls_per_tick, B, dev):
+    """mpc_controller_cusadi.py:97-203 restated for measurement (everything between the marshalled inputs and the wrench),
+    with `calls_per_tick` solver calls (4 for a 5-iteration kernel, 20 for the one-iteration build of oracle/_ref)."""
+    import torch
+    former.evaluate(inputs)
+    H = former.getDenseOutput(0); f = former.getDenseOutput(1).squeeze(-1); A = former.getDenseOutput(2)
+    b = former.getDenseOutput(3).squeeze(-1); G = former.getDenseOutput(4); d = former.getDenseOutput(5).squeeze(-1)
+    Hs, fs, As, bs, Gs, ds = former.outputs_sparse
+    H_col = Hs.double().contiguous(); G_col = Gs.double().contiguous(); A_col = As.double().contiguous()
+    f_col = fs.reshape(B, -1, 1).double().contiguous(); d_col = ds.reshape(B, -1, 1).double().contiguous()
+    b_col = bs.reshape(B, -1, 1).double().contiguous()
+    nz, num_eq, num_ineq = H.shape[1], A.shape[1], G.shape[1]
+    x = torch.zeros(B, nz, device=dev, dtype=torch.float64)
+    s = torch.maximum(d - (G @ x.unsqueeze(2)).squeeze(2), torch.ones_like(d))
+    z = torch.ones(B, num_ineq, device=dev, dtype=torch.float64)
+    y = torch.ones(B, num_eq, device=dev, dtype=torch.float64)
+    for _ in range(calls_per_tick):
+        solver.evaluate([H_col, G_col, A_col, f_col, d_col, b_col, x.double().reshape(B, -1, 1).contiguous(),
+                         s.double().reshape(B, -1, 1).contiguous(), z.double().reshape(B, -1, 1).contiguous(),
+                         y.double().reshape(B, -1, 1).contiguous()])
+        x = solver.getDenseOutput(0).reshape(B, -1).clone().detach(); s = solver.getDenseOutput(1).reshape(B, -1).clone().detach()
+        z = solver.getDenseOutput(2).reshape(B, -1).clone().detach(); y = solver.getDenseOutput(3).reshape(B, -1).clone().detach()
+    sol = x.clone().detach()
+    u = sol[:, 120:132]
+    lf, rf, lm, rm = u[:, :3].float(), u[:, 3:6].float(), u[:, 6:9].float(), u[:, 9:12].float()
+    lm[:, 0] = 0.0; rm[:, 0] = 0.0
+    Rt = rot.transpose(1, 2)
+    parts = [-(Rt @ v.unsqueeze(-1)).squeeze(-1) for v in (lf, lm, rf, rm)]
+    return torch.cat(parts, dim=1).reshape(-1, 2, 6).float()
+
+
+def run_compat(args, emit=True, ticks=5):
+    """`--impl compat`: what a maintainer gets who ONLY swaps the two shared objects and leaves
+    CusadiFunction and MPCControllerCusadi.run() untouched: the reference tick (form + 4 x 5 iterations) at 4 096 envs
+    through this repo's libqp_former.so / libsparse_pdipm_multiple_iterations.so, called exactly as the unmodified host
+    code calls them -- next to the same host code over the reference's own generated kernels (oracle/_ref), and next to
+    this repo's fused tick (srbd_mpc_solve, 20 iterations)."""
+    import torch
+    import biped_pympc_b200 as bp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cusadi_ref
+    dev, B = "cuda:0", args.envs
+    inp, rot = bp.workload.make_batch(B, seed=20261018)
+    ins = [torch.as_tensor(a, device=dev) for a in inp]
+    rot_t = torch.as_tensor(rot, dtype=torch.float32, device=dev)
+    # work tensor an unmodified CusadiFunction allocates and zero-fills: B x fn.sz_w() doubles; sz_w of the reference's
+    # functions as built from its sources (oracle/_ref/*.meta), else the figures DESIGN.md section 1 records
+    meta = {}
+    for name, suffix, default in (("qp_former", "", 2179), ("sparse_pdipm_multiple_iterations", "", 7763)):
+        path = os.path.join(cusadi_ref.REF_DIR, f"{name}{suffix}.meta")
+        try:
+            meta[name] = int(dict(line.split() for line in open(path))["sz_w"])
+        except Exception:
+            meta[name] = default
+    libdir = os.path.dirname(bp._native.LIB_PATH)
+
+    def measure(former, solver, calls):
+        w = None
+        for _ in range(2):
+            w = compat_tick(former, solver, ins, rot_t, calls, B, dev)
+        torch.cuda.synchronize()
+        former.kernel_s = solver.kernel_s = 0.0
+        t0 = time.perf_counter()
+        for _ in range(ticks):
+            w = compat_tick(former, solver, ins, rot_t, calls, B, dev)
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0) / ticks
+        return ms, 1e3 * former.kernel_s / ticks, 1e3 * solver.kernel_s / ticks, w
+
+    ours_f = _CompatFunction(bp.QP_FORMER_FUNCTION, B, libdir, meta["qp_former"], dev)
+    ours_s = _CompatFunction(bp.PDIPM_FUNCTION, B, libdir, meta["sparse_pdipm_multiple_iterations"], dev)
+    ms, kf, ks, w = measure(ours_f, ours_s, 4)
+    # the .so calls alone, same calling convention (zero-fill included), without the dense host-side work around them
+    for o in (ours_f, ours_s):
+        o.kernel_s = 0.0
+    Hs, fs, As, bs, Gs, ds = ours_f.outputs_sparse
+    x = torch.zeros(B, 240, dtype=torch.float64, device=dev); y = torch.ones(B, 140, dtype=torch.float64, device=dev)
+    sv = torch.maximum(ds, torch.ones_like(ds)); z = torch.ones_like(ds)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(ticks):
+        ours_f.evaluate(ins)
+        cur = [x, sv, z, y]
+        for _ in range(4):
+            ours_s.evaluate([Hs, Gs, As, fs, ds, bs, *cur])
+            cur = [t.clone() for t in ours_s.outputs_sparse[:4]]
+    torch.cuda.synchronize()
+    calls_ms = 1e3 * (time.perf_counter() - t0) / ticks
+    # this repo's fused tick on the same inputs: the wrench must agree (same 20 iterations)
+    ctx = bp.Context(B, 0)
+    wf = ctx.solve(ins, rot_t, num_calls=4, iters_per_call=5)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        wf = ctx.solve(ins, rot_t, num_calls=4, iters_per_call=5)
+    torch.cuda.synchronize()
+    fused_ms = 1e3 * (time.perf_counter() - t0) / 20
+    agree = float((w - wf).abs().max() / wf.abs().max())
+    ctx.close()
+    rec = {"impl": "compat", "metric": "mpc_ticks_per_sec_4096_envs_4x5_iters_unmodified_host_code", "unit": "ticks/s (one env, one tick)",
+           "value": B / (ms * 1e-3), "ms_per_tick": ms, "n_gpus": 1, "envs": B, "ticks_timed": ticks, "higher_is_better": True,
+           "dtype": "f64", "data": "synthetic",
+           "what": "the reference tick (qp_former + 4 x sparse_pdipm_multiple_iterations, mpc_controller_cusadi.py:97-203) through this "
+                   "repo's two drop-in .so files, host code unmodified: zero-filled outputs and work tensor per call, 6 + 16 getDenseOutput "
+                   "(sparse_coo -> dense), dense G @ x cold start, clones",
+           "kernel_ms_per_tick": {"qp_former": kf, "sparse_pdipm_multiple_iterations_x4": ks},
+           "evaluate_calls_only_ms_per_tick": calls_ms,
+           "host_side_share": 1.0 - (kf + ks) / ms,
+           "work_doubles_per_env_zero_filled": meta,
+           "fused_tick_ms": fused_ms, "fused_tick_speedup_over_dropin": ms / fused_ms,
+           "wrench_vs_fused_tick_rel": agree}
+    var = cusadi_ref.solver_variant()
+    if var is not None and cusadi_ref.available("qp_former"):
+        suffix, per_call = var
+        ref_f = _CompatFunction(bp.QP_FORMER_FUNCTION, B, cusadi_ref.REF_DIR, meta["qp_former"], dev)
+        sz = int(dict(line.split() for line in open(os.path.join(cusadi_ref.REF_DIR, f"sparse_pdipm_multiple_iterations{suffix}.meta")))["sz_w"])
+        ref_s = _CompatFunction(bp.PDIPM_FUNCTION, B, cusadi_ref.REF_DIR, sz, dev, suffix)
+        ticks_ref, ticks = ticks, 2
+        rms, rkf, rks, rw = measure(ref_f, ref_s, 20 // per_call)
+        ticks = ticks_ref
+        rec["reference_cusadi_same_host_code"] = {
+            "ms_per_tick": rms, "kernel_ms_per_tick": {"qp_former": rkf, "solver": rks}, "solver_calls_per_tick": 20 // per_call,
+            "what": "the same host code over the reference's own generated kernels (oracle/_ref)"
+                    + ("" if per_call == 5 else "; solver = its function built with num_iters=1, 20 calls per tick"),
+            "dropin_speedup": rms / ms, "wrench_vs_dropin_rel": float((rw - w).abs().max() / w.abs().max())}
+    if emit:
+        print(json.dumps(rec))
+    return rec
+
 
 
 def run_b200(args):
@@ -307,10 +568,29 @@ def run_b200(args):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    clocks = sampler.stop(t_wall0, t_wall1)
     e2e_value = world * B * n_e2e / e2e_s
     h2d = sum(a.numel() * 8 for a in h_in if a is not None) + h_rot.numel() * 4
     d2h = h_w.numel() * 4
+
+    # ---- p50 / p99 step latency (the metric's second half; SURVEY 8d: 1 000 repetitions after 50 warm-ups, CUDA events
+    #      around the stream work of one batched call, L2 flushed between repetitions) -------------------------------
+    for _ in range(50):
+        step()
+    lat_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.latency_reps)]
+    torch.cuda.synchronize()
+    t_lat0 = time.time()
+    for a, b in lat_ev:
+        flush.fill_(1.0)
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    t_lat1 = time.time()
+    lat_ms = sorted(a.elapsed_time(b) for a, b in lat_ev)
+    # clocks and throttle reasons: sampled over the K timed steps AND the latency loop (the K steps alone are shorter than
+    # one 20 ms sampling period at the default K)
+    clocks = sampler.stop(t_wall0, t_lat1)
+    clocks["window"] = "timed steps + latency loop" if clocks.get("window") == "timed region" else clocks.get("window")
 
     default_wl = (args.calls == 1 and args.iters == ITERS and args.tol <= 0)
     line = {
@@ -329,12 +609,18 @@ def run_b200(args):
         "clocks": clocks,
     }
     ts = sorted(times_ms)
-    line["latency_ms"] = {"p50": ts[len(ts) // 2], "p99": ts[min(len(ts) - 1, int(0.99 * len(ts)))], "max": ts[-1]}
+    pct = lambda v, q: v[min(len(v) - 1, int(q * len(v)))]  # noqa: E731
+    line["latency_ms"] = {"p50": pct(lat_ms, 0.50), "p99": pct(lat_ms, 0.99), "max": lat_ms[-1], "repetitions": len(lat_ms),
+                          "what": "one batched call (CUDA events on its stream), separate loop after 50 warm-ups, L2 flushed between calls",
+                          "timed_steps": {"p50": pct(ts, 0.50), "p99": pct(ts, 0.99), "max": ts[-1], "n": len(ts)}}
 
     if iters_done is not None:
         hist = torch.bincount(iters_done.clamp(min=0).to(torch.int64), minlength=args.calls * args.iters + 1).tolist()
         line["iterations_histogram"] = {str(i): c for i, c in enumerate(hist) if c}
     n_it = args.calls * args.iters
+    subs = default_wl and not args.no_sub
+    if subs:                      # every rank takes part (65 536 / N envs each)
+        line["strong_scaling_65536"] = sub_strong_scaling(bp, torch, dist, dev, local_rank, rank, world, flush)
     if rank == 0:
         # ---- roofline of the dominant kernel (PDIPM), timed alone with CUDA events -------------
         peaks, peak_src = _peaks()
@@ -403,20 +689,44 @@ def run_b200(args):
                                      "peak_source": f"{sms} SMs x 1 wavefront/clk x the SM clock sampled in this run ({clk['sm_mhz']:.0f} MHz)",
                                      "source": cap.get("capture")}
         ach_bw = B * BYTES_ASSEMBLY / (fm_ms * 1e-3) / 1e9
-        line["roofline_assembly"] = {"kernel": "qp_form_kernel", "bound": "hbm", "achieved": ach_bw,
-                                     "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                                     "frac": ach_bw / peaks.get("hbm_gbs", 6650.0),
-                                     "traffic": cap.get("assembly_dram_bytes_per_launch"),
-                                     "traffic_note": "DRAM bytes of one launch from profiles/ncu_qpform_r1_4096_summary.csv: below the "
-                                                     f"{B * BYTES_ASSEMBLY} algorithmic bytes because most of the output is still in L2 at kernel end",
-                                     "kernel_ms": fm_ms, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)"}
+        asm_small = {"kernel": "qp_form_kernel", "envs": B, "bound": "launch latency + L2 (the 88.7 MB of output stay in the 126 MB L2: not an HBM-bound launch)",
+                     "achieved": ach_bw, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": ach_bw / peaks.get("hbm_gbs", 6650.0),
+                     "traffic": cap.get("assembly_dram_bytes_per_launch"),
+                     "traffic_note": "DRAM bytes of one launch from profiles/ncu_qpform_r1_4096_summary.csv: below the "
+                                     f"{B * BYTES_ASSEMBLY} algorithmic bytes because most of the output is still in L2 at kernel end",
+                     "kernel_ms": fm_ms, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)"}
+        if subs:
+            # the assembly kernel's HBM roofline is quoted where the launch IS HBM-bound: 65 536 envs (1.4 GB per launch)
+            B65 = 65536
+            ins65 = [t.repeat((B65 + B - 1) // B, 1)[:B65].contiguous() for t in ins]
+            qp65 = bp.qp_form(ins65)
+            f65 = []
+            for i in range(8):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                bp.qp_form(ins65, out=qp65)
+                b.record()
+                b.synchronize()
+                if i >= 3:
+                    f65.append(a.elapsed_time(b))
+            ms65 = sum(f65) / len(f65)
+            bw65 = B65 * BYTES_ASSEMBLY / (ms65 * 1e-3) / 1e9
+            line["roofline_assembly"] = {"kernel": "qp_form_kernel", "envs": B65, "bound": "hbm", "achieved": bw65, "peak": peaks.get("hbm_gbs"),
+                                         "unit": "GB/s", "frac": bw65 / peaks.get("hbm_gbs", 6650.0), "traffic": None, "kernel_ms": ms65,
+                                         "algorithmic": f"{BYTES_ASSEMBLY} B/env x {B65} envs (inputs and outputs larger than L2: no flush needed)",
+                                         "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)", "at_metric_batch": asm_small}
+            del ins65, qp65
+        else:
+            line["roofline_assembly"] = asm_small
         # ---- CPU baseline on the box's host cores (bounded sample) -----------------------------
         if world == 1 and default_wl:
             threads = os.cpu_count() or 1
-            sample = 2048
-            cpu_val, _, kind, desc = cpu_reference_run(sample, ITERS, 3, 1, threads)
+            cpu_val, _, kind, desc = cpu_reference_run(B, ITERS, 3, 1, threads)
             line["cpu_baseline"] = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": kind,
-                                    "sample": f"{sample} envs x 3 steps of the same workload; {desc}"}
+                                    "sample": f"the metric's full batch, {B} envs x 3 steps of the same seeded workload; {desc}"}
+            port_val, _, _, port_desc = cpu_reference_run(B, ITERS, 3, 1, threads, want="port")
+            line["cpu_baseline_port"] = {"value": port_val, "unit": UNIT, "cores": threads, "kind": "port",
+                                         "sample": f"{B} envs x 3 steps; {port_desc}"}
             # the reference's CusADi GPU path on this GPU, same workload (north_star: "next to the reference's CusADi GPU
             # path where it can be compiled offline"); see run_cusadi_ref / oracle/make_cusadi_ref.py for what it is
             try:
@@ -430,6 +740,30 @@ def run_b200(args):
                                                    "what": cu["config"]["workload"] + "; " + cu["config"]["solver_kernel"]}
             except Exception as exc:      # a missing / broken baseline library must not take the bench line down
                 line["cusadi_gpu_baseline"] = {"unavailable": repr(exc)}
+        if world == 1 and subs:
+            # ---- the e2e leg's other cases: every one of the 17 buffers passed (x, u included: byte for byte what the
+            #      reference hands to qp_former), pinned and pageable (cudaMemcpyAsync staging path) ----------------------
+            def e2e_case(pin):
+                mk = (lambda t: t.pin_memory()) if pin else (lambda t: t)
+                hi = [mk(torch.as_tensor(a).clone()) for a in inp]
+                hr, hw = mk(torch.as_tensor(rot, dtype=torch.float32).clone()), mk(torch.empty((B, 2, 6), dtype=torch.float32))
+                for _ in range(3):
+                    ctx.solve_host(hi, hr, hw, num_calls=args.calls, iters_per_call=args.iters)
+                t0 = time.perf_counter()
+                for _ in range(20):
+                    ctx.solve_host(hi, hr, hw, num_calls=args.calls, iters_per_call=args.iters)
+                dt = (time.perf_counter() - t0) / 20
+                return {"value": B / dt, "unit": UNIT, "ms_per_step": 1e3 * dt, "steps": 20,
+                        "h2d_bytes_per_step": sum(a.numel() * 8 for a in hi) + hr.numel() * 4, "d2h_bytes_per_step": hw.numel() * 4}
+            line["e2e_all17_pinned"] = e2e_case(True)
+            line["e2e_all17_pageable"] = e2e_case(False)
+            for key, fn in (("converge_16384", lambda: sub_converge(bp, torch, dev, local_rank, flush)),
+                            ("closed_loop_4096x1000", sub_closed_loop),
+                            ("compat_dropin", lambda: run_compat(argparse.Namespace(envs=B), emit=False))):
+                try:
+                    line[key] = fn()
+                except Exception as exc:      # a sub-record must not take the bench line down
+                    line[key] = {"unavailable": repr(exc)}
         sys.stdout.flush()
         if saved_stdout is not None:
             os.dup2(saved_stdout, 1)
@@ -461,7 +795,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cusadi"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cusadi", "compat"])
+    ap.add_argument("--latency-reps", type=int, default=1000, help="repetitions of the p50 / p99 latency loop")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (other BASELINE configs, drop-in, closed loop)")
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     # other BASELINE configs (not the default bench line): --calls 4 = the reference tick (4 x 5 iterations,
     # mpc_controller_cusadi.py:144-169); --envs 16384 --iters 30 --tol 1e-8 = run to convergence (config 4)
@@ -481,6 +817,9 @@ def main():
     elif args.impl == "cusadi":
         if int(os.environ.get("RANK", "0")) == 0:
             run_cusadi_ref(args)
+    elif args.impl == "compat":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_compat(args)
     else:
         run_b200(args)
 

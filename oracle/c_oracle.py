@@ -59,5 +59,25 @@ def pdipm(qp, iters, x=None, s=None, z=None, y=None, nthreads=0, long_double=Fal
     return outs
 
 
+def pdipm_tol(qp, max_iters, tol, x=None, s=None, z=None, y=None, nthreads=0, long_double=False):
+    """Tolerance mode: env e stops after the first iteration whose (|rx|, |rs|, |re|, mu) are all < tol
+    (generate_solver_function.py:187; pre-step residual norms + post-step mu, sparse_pdipm_solver.py:524-530),
+    at most max_iters.  Returns (outs6, iters_done)."""
+    L = lib(long_double)
+    fn = L.srbd_oracle_pdipm_tol_ld if long_double else L.srbd_oracle_pdipm_tol
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                   ctypes.c_int, ctypes.c_int]
+    Hv, f, Av, b, Gv, d = qp
+    B = Hv.shape[0]
+    cold = x is None
+    z0 = lambda n: np.zeros((B, n))
+    ins, inp = _arr([Hv, Gv, Av, f, d, b, z0(240) if cold else x, z0(160) if cold else s,
+                     z0(160) if cold else z, z0(140) if cold else y])
+    outs, outp = _arr([np.zeros((B, n)) for n in (240, 160, 160, 140, 4, 1)])
+    itd = np.zeros(B, dtype=np.int32)
+    fn(inp, outp, itd.ctypes.data_as(ctypes.c_void_p), B, int(max_iters), float(tol), int(cold), nthreads)
+    return outs, itd
+
+
 def kkt_fill():
     return lib().srbd_oracle_kkt_fill()

@@ -238,14 +238,15 @@ static REAL ratio_step(const REAL* v, const REAL* dv, int n) {
 static void pdipm_env(const double* Qv, const double* Gv, const double* Av, const double* f, const double* h,
                       const double* b, const double* x0, const double* s0, const double* z0, const double* y0,
                       double* xo, double* so, double* zo, double* yo, double* res, double* muo,
-                      int iters, LdlWork* w) {
+                      int iters, LdlWork* w, double tol, int* it_done) {
   REAL x[NZ], s[NINEQ], z[NINEQ], y[NEQ], rx[NZ], rs[NINEQ], re[NEQ];
   REAL rhs[NKKT], aff[NKKT], cor[NKKT], ds[NINEQ], dz[NINEQ];
   for (int i = 0; i < NZ; ++i) x[i] = x0[i];
   for (int i = 0; i < NINEQ; ++i) { s[i] = s0[i]; z[i] = z0[i]; }
   for (int i = 0; i < NEQ; ++i) y[i] = y0[i];
   REAL mu_new = 0;
-  for (int it = 0; it < iters; ++it) {
+  int it = 0;
+  for (; it < iters; ++it) {
     /* residuals (:392-402) */
     for (int j = 0; j < NZ; ++j) rx[j] = (REAL)Qv[j] * x[j] + (REAL)f[j];
     for (int i = 0; i < NINEQ; ++i) rs[i] = s[i] - (REAL)h[i];
@@ -296,7 +297,17 @@ static void pdipm_env(const double* Qv, const double* Gv, const double* Av, cons
       mu_new += s[i] * z[i];
     }
     mu_new /= (REAL)NINEQ;
+    /* tolerance mode: the criterion of generate_solver_function.py:187 on the quantities one call returns --
+     * the residual norms of THIS iteration's starting point (:524-529) and the post-step mu (:530) */
+    if (tol > 0) {
+      REAL tx = 0, ts = 0, te = 0;
+      for (int j = 0; j < NZ; ++j) tx += rx[j] * rx[j];
+      for (int i = 0; i < NINEQ; ++i) ts += rs[i] * rs[i];
+      for (int i = 0; i < NEQ; ++i) te += re[i] * re[i];
+      if ((double)RSQRT(tx) < tol && (double)RSQRT(ts) < tol && (double)RSQRT(te) < tol && (double)mu_new < tol) { ++it; break; }
+    }
   }
+  if (it_done) *it_done = it;
   REAL nx = 0, ns = 0, ne = 0;
   if (iters > 0) {
     for (int j = 0; j < NZ; ++j) nx += rx[j] * rx[j];
@@ -312,7 +323,20 @@ static void pdipm_env(const double* Qv, const double* Gv, const double* Av, cons
 
 /* in10: Q_val G_val A_val f h b x s z y ; out6: x s z y residuals(4) mu(1) ; (B, nnz) row-major.
  * cold_start != 0: x=0, s=max(h - G*0, 1), z=1, y=1 (mpc_controller_cusadi.py:138-141). */
+static int pdipm_batch(const double* const* in10, double* const* out6, int B, int iters, int cold_start, int nthreads,
+                       double tol, int* iters_done);
 int FN(srbd_oracle_pdipm)(const double* const* in10, double* const* out6, int B, int iters, int cold_start, int nthreads) {
+  return pdipm_batch(in10, out6, B, iters, cold_start, nthreads, 0.0, NULL);
+}
+/* the same with a convergence tolerance (runtime extension of this repo's kernels; criterion of
+ * generate_solver_function.py:187): env e stops after the first iteration whose (|rx|, |rs|, |re|, mu) are all < tol,
+ * at most `iters`; iters_done[e] = iterations executed. */
+int FN(srbd_oracle_pdipm_tol)(const double* const* in10, double* const* out6, int* iters_done, int B, int iters, double tol,
+                              int cold_start, int nthreads) {
+  return pdipm_batch(in10, out6, B, iters, cold_start, nthreads, tol, iters_done);
+}
+static int pdipm_batch(const double* const* in10, double* const* out6, int B, int iters, int cold_start, int nthreads,
+                       double tol, int* iters_done) {
   ensure_ready();
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -336,7 +360,8 @@ int FN(srbd_oracle_pdipm)(const double* const* in10, double* const* out6, int B,
       pdipm_env(in10[0] + (size_t)e * NNZ_H, in10[1] + (size_t)e * NNZ_G, in10[2] + (size_t)e * NNZ_A,
                 in10[3] + (size_t)e * NZ, h, in10[5] + (size_t)e * NEQ, x0, s0, z0, y0,
                 out6[0] + (size_t)e * NZ, out6[1] + (size_t)e * NINEQ, out6[2] + (size_t)e * NINEQ,
-                out6[3] + (size_t)e * NEQ, out6[4] + (size_t)e * 4, out6[5] + (size_t)e, iters, &w);
+                out6[3] + (size_t)e * NEQ, out6[4] + (size_t)e * 4, out6[5] + (size_t)e, iters, &w, tol,
+                iters_done ? iters_done + e : NULL);
     }
     ldl_free(&w);
   }

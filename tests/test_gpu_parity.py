@@ -189,6 +189,109 @@ def test_tolerance_mode_and_iteration_counts(batch64):
     assert all(1 <= v <= 30 for v in itd.tolist())
 
 
+def test_tolerance_mode_stops_each_env_at_the_oracles_iteration():
+    """BASELINE configs[3] semantics: with tol > 0 an env stops after the first iteration whose pre-step residual
+    norms and post-step mu are all < tol (generate_solver_function.py:187).  Standing envs with a loose tolerance stop
+    at DIFFERENT intermediate iterations (21 ... 30 of 30): the kernel must stop every env at the oracle's iteration
+    and return the oracle's iterate there.  After 21-30 iterations the reference formulation itself, evaluated in
+    fp64, is 1e-7 ... 1e-6 away from its 80-bit evaluation on these envs; the kernel has to be at least as
+    close as that, and within 5e-8 in absolute terms (measured: 9e-9)."""
+    inp, _ = bp.workload.make_batch(48, seed=7, standing=True)
+    qp = co.qp_former(inp)
+    tol = 1e-1
+    ref, it_ref = co.pdipm_tol(qp, 30, tol, long_double=True)
+    dbl, it_d = co.pdipm_tol(qp, 30, tol)
+    assert len(set(it_ref.tolist())) >= 4 and it_ref.min() < 30          # the test is about intermediate stops
+    clear = it_ref == it_d                                                # 64-bit and 80-bit oracle agree on the count
+    assert clear.mean() > 0.9
+    Hv, f, Av, b, Gv, d = _dev(qp)
+    for fast in (True, False):
+        itd = torch.full((48,), -7, dtype=torch.int32, device=DEV)
+        out = bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=30, tol=tol, cold_start=True, stage_invariant=fast, iters_done=itd)
+        got_it = itd.cpu().numpy()
+        assert np.array_equal(got_it[clear], it_ref[clear]), (fast, got_it, it_ref)
+        for i, n in enumerate("xszy"):
+            g = out[i].cpu().numpy()
+            e_k = max(rel_err(g[e:e + 1], ref[i][e:e + 1]) for e in np.nonzero(clear)[0])
+            e_d = max(rel_err(dbl[i][e:e + 1], ref[i][e:e + 1]) for e in np.nonzero(clear)[0])
+            assert e_k <= max(TOL_IP, e_d) and e_k < 5e-8, (fast, n, e_k, e_d)
+        # the reported residuals are those of the stopping iteration
+        assert np.allclose(out[4].cpu().numpy()[clear], ref[4][clear], rtol=1e-6, atol=1e-12)
+    # through the fused tick as well
+    ins = _dev(inp)
+    ctx = bp.Context(48)
+    itd = torch.zeros(48, dtype=torch.int32, device=DEV)
+    x = ctx.solve(ins, torch.eye(3, device=DEV).repeat(48, 1, 1), num_calls=1, iters_per_call=30, tol=tol, want_iterates=True,
+                  iters_done=itd)[1]
+    assert np.array_equal(itd.cpu().numpy()[clear], it_ref[clear])
+    assert rel_err(x.cpu().numpy()[clear], ref[0][clear]) < 5e-8
+    ctx.close()
+
+
+# per-iteration parity against the 80-bit oracle: (iterations, tolerance on x s z y).  DESIGN.md section 5: <= 1e-9 at
+# the reference's 5 iterations (5e-9 on x after the very first step from the y = 1 cold start); beyond 10 iterations on
+# walking contact tables the reference's own fp64 evaluation is only reproducible to 1e-8 ... 1e-4, which is what the
+# second bound (10 x the 64-bit oracle's own distance from the 80-bit one) expresses
+PARITY_CURVE = ((1, 5e-9), (2, 1e-9), (3, 1e-9), (5, 1e-9), (10, 1e-8), (15, 1e-7), (20, 2e-4), (30, 2e-3))
+
+
+def test_parity_curve_1_to_30_iterations():
+    inp, _ = bp.workload.make_batch(16, seed=99)
+    qp = co.qp_former(inp)
+    Hv, f, Av, b, Gv, d = _dev(qp)
+    worst = {}
+    for iters, tol in PARITY_CURVE:
+        ref = co.pdipm(qp, iters, long_double=True)
+        dbl = co.pdipm(qp, iters)
+        out = _np(bp.pdipm([Hv, Gv, Av, f, d, b], num_iters=iters, cold_start=True, stage_invariant=True))
+        for i, n in enumerate("xszy"):
+            e_k = max(rel_err(out[i][e:e + 1], ref[i][e:e + 1]) for e in range(16))
+            e_d = max(rel_err(dbl[i][e:e + 1], ref[i][e:e + 1]) for e in range(16))
+            worst[(iters, n)] = (e_k, e_d)
+            assert e_k <= tol, (iters, n, e_k)
+            assert e_k <= max(1e-9, 10.0 * e_d) or iters == 1, (iters, n, e_k, e_d)
+    # standing envs (all feet in contact): 1e-9 up to 10 iterations, and never farther from the 80-bit oracle than the
+    # reference formulation evaluated in fp64 is
+    st, _ = bp.workload.make_batch(8, seed=3, standing=True)
+    qps = co.qp_former(st)
+    dv = _dev(qps)
+    for iters in (5, 10, 20, 30):
+        ref = co.pdipm(qps, iters, long_double=True)
+        dbl = co.pdipm(qps, iters)
+        out = _np(bp.pdipm([dv[0], dv[4], dv[2], dv[1], dv[5], dv[3]], num_iters=iters, cold_start=True, stage_invariant=True))
+        for i in range(4):
+            assert rel_err(out[i], ref[i]) <= max(TOL_IP if iters <= 10 else 1e-8, rel_err(dbl[i], ref[i])), (iters, i)
+
+
+@pytest.mark.parametrize("B,seed", [(4096, 20261018), (16384, 20261019)])
+def test_full_baseline_batch_against_the_oracle(B, seed):
+    """The whole BASELINE batch (configs[1]: 4 096 envs of the bench seed; and a 16 384-env batch, configs[3]'s size)
+    through the fused tick, EVERY env against the 80-bit oracle at the reference's 5 iterations, assembly included.
+    Bar: <= 1e-9 per env and output vector -- except on the few envs where the reference formulation itself, evaluated
+    in fp64 (oracle/srbd_oracle.c, double build), is farther than 1e-9 from its own 80-bit evaluation (env 798 of the
+    bench batch: 1.8e-9 on x): there the kernel must be at least as close to the 80-bit value as the reference's fp64
+    evaluation is.  At most 0.1 % of the envs may be of that kind."""
+    inp, rot = bp.workload.make_batch(B, seed=seed)
+    qp = co.qp_former(inp)
+    ref = co.pdipm(qp, 5, long_double=True)
+    dbl = co.pdipm(qp, 5)
+    ins = _dev(inp)
+    _check_qp(_np(bp.qp_form(ins)), qp)
+    ctx = bp.Context(B)
+    out = ctx.solve(ins, torch.as_tensor(rot, dtype=torch.float32, device=DEV), num_calls=1, iters_per_call=5, want_iterates=True)
+    over = np.zeros(B, bool)
+    for i, n in enumerate("xszy"):
+        g = out[1 + i].cpu().numpy()
+        nrm = np.maximum(np.linalg.norm(ref[i], axis=1), 1e-300)
+        err = np.linalg.norm(g - ref[i], axis=1) / nrm
+        err_ref64 = np.linalg.norm(dbl[i] - ref[i], axis=1) / nrm
+        bad = err > np.maximum(TOL_IP, err_ref64)
+        assert not bad.any(), (n, int(bad.sum()), float(err.max()), int(err.argmax()), float(err_ref64[err.argmax()]))
+        over |= err > TOL_IP
+    assert over.mean() <= 1e-3, int(over.sum())
+    ctx.close()
+
+
 def test_cusadi_compatible_evaluate(golden):
     """lib<fn>.so::evaluate with DEVICE arrays of device pointers (CusadiFunction.py:84-92)."""
     import os
@@ -288,8 +391,9 @@ def test_controller_run_matches_oracle_tick():
     c.init_solver()
     wrench, cost = c.run()
     assert tuple(wrench.shape) == (B, 2, 6) and wrench.dtype == torch.float32 and tuple(cost.shape) == (B,)
-    # oracle: same marshalling (I_world recomputed in fp32 like the reference does)
-    ins = [t.cpu().numpy() for t in bp.mpc_controller_b200.marshal_inputs_torch(c)]
+    # oracle: same marshalling (I_world recomputed in fp32 like the reference does); the controller's defaults are the
+    # reference's three layout quirks (reference_quirks = True: Q1, Q2 and the stride-12 read of the 13-long Q)
+    ins = [t.cpu().numpy() for t in bp.mpc_controller_b200.marshal_inputs_torch(c, reproduce_q_stride_bug=True)]
     qp = co.qp_former(ins)
     it = co.pdipm(qp, 20, long_double=True)
     from oracle import srbd_oracle as so

@@ -104,3 +104,28 @@ def test_pdipm_converges_to_the_kkt_point_of_the_qp():
         assert np.abs(z * (d - G @ x)).max() < 1e-4                         # complementarity
     # and the optimum carries the weight: sum of vertical forces of stage 0 within 15 % of m g
     assert abs(x[122] + x[125] - 40.0 * 9.81) < 0.15 * 40.0 * 9.81
+
+
+def test_tolerance_mode_of_the_oracle_and_of_the_device_code():
+    """generate_solver_function.py:187 as a runtime mode: an env stops after the first iteration whose pre-step residual
+    norms and post-step mu are below tol.  (i) stopping at iteration n returns exactly the n-iteration iterate; (ii) the
+    kernel's device code (under the warp emulator) stops every env at the oracle's iteration, at different intermediate
+    iterations across the batch."""
+    import biped_pympc_b200 as bp
+    from helpers import emul_pdipm
+    inp, _ = bp.workload.make_batch(12, seed=7, standing=True)
+    qp = co.qp_former(inp)
+    out, it = co.pdipm_tol(qp, 30, 1e-1)
+    assert it.min() < 30 and len(set(it.tolist())) >= 3
+    for e in (0, 5, 11):
+        fixed = co.pdipm([a[e:e + 1] for a in qp], int(it[e]))
+        for i in range(5):
+            assert np.array_equal(fixed[i][0], out[i][e])
+        assert (out[4][e] < 1e-1).all() or it[e] == 30
+    capped, itc = co.pdipm_tol(qp, 7, 1e-30)            # never satisfied: the cap
+    assert (itc == 7).all() and np.array_equal(capped[0], co.pdipm(qp, 7)[0])
+    ref, it_ld = co.pdipm_tol(qp, 30, 1e-1, long_double=True)
+    got, itd = emul_pdipm(qp, 30, tol=1e-1, uniform=True)
+    assert np.array_equal(itd, it_ld) and np.array_equal(it, it_ld)
+    for i in range(4):
+        assert rel_err(got[i], ref[i]) < 5e-8

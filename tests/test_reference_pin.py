@@ -279,7 +279,7 @@ def test_compiled_tapes_of_the_reference_functions_reproduce_the_fixture(ref):
     import cusadi_ref
     if not cusadi_ref.cpu_available():
         pytest.skip("oracle/_ref/lib*_cpu.so not built (python oracle/make_cusadi_ref.py --target cpu)")
-    cpu = cusadi_ref.CusadiRefCpu()
+    cpu = cusadi_ref.CusadiRefCpu(prefer_o3=False)     # the -O1 build: no FMA contraction, bit-identical to the fixture
     qp = cpu.qp_former(_inputs(ref))
     for n, v in zip("HfAbGd", qp):
         assert np.array_equal(v, ref[f"qp_{n}"]), n
