@@ -28,7 +28,7 @@ _PP = ctypes.POINTER(_P)
 EXPORTED_SYMBOLS = (
     "srbd_version", "srbd_error_string", "srbd_last_cuda_error", "srbd_init",
     "srbd_qp_former_nnz_in", "srbd_qp_former_nnz_out", "srbd_pdipm_nnz_in", "srbd_pdipm_nnz_out",
-    "srbd_pattern", "srbd_loop_buffers_size", "srbd_update_state", "srbd_lowlevel", "srbd_gait", "srbd_reference_trajectory", "srbd_marshal_inputs", "srbd_qp_form", "srbd_pdipm_work_doubles", "srbd_pdipm", "srbd_pdipm_is_stage_invariant", "srbd_wrench",
+    "srbd_pattern", "srbd_loop_buffers_size", "srbd_update_state", "srbd_lowlevel", "srbd_gait", "srbd_reference_trajectory", "srbd_marshal_inputs", "srbd_marshal_inputs_iw", "srbd_qp_form", "srbd_pdipm_work_doubles", "srbd_pdipm", "srbd_pdipm_is_stage_invariant", "srbd_wrench",
     "srbd_ctx_create", "srbd_ctx_destroy", "srbd_mpc_solve", "srbd_mpc_solve_warm", "srbd_mpc_solve_host",
     "srbd_qp_former_evaluate", "srbd_sparse_pdipm_multiple_iterations_evaluate", "srbd_dfma_peak",
 )
@@ -63,6 +63,7 @@ def load(build_if_missing: bool = True):
     lib.srbd_pdipm.argtypes = [vp, vp, vp, vp, ci, ci, cd, cu, vp]
     lib.srbd_pdipm_is_stage_invariant.argtypes = [vp, ci, vp, ctypes.POINTER(ci)]
     lib.srbd_marshal_inputs.argtypes = [vp, ci, ci, ci, cd, cd, vp, ci, vp]
+    lib.srbd_marshal_inputs_iw.argtypes = [vp, vp, vp, ci, ci, ci, cd, cd, vp, ci, vp]
     lib.srbd_wrench.argtypes = [vp, vp, vp, ci, vp]
     lib.srbd_loop_buffers_size.restype = ctypes.c_size_t
     lib.srbd_update_state.argtypes = [vp, vp, ci, ci, vp]
@@ -72,7 +73,7 @@ def load(build_if_missing: bool = True):
     lib.srbd_ctx_create.argtypes = [ctypes.POINTER(vp), ci, ci]
     lib.srbd_ctx_destroy.argtypes = [vp]
     lib.srbd_mpc_solve.argtypes = [vp, vp, vp, ci, ci, ci, cd, vp, vp, vp, vp, vp, vp, vp, vp]
-    lib.srbd_mpc_solve_warm.argtypes = [vp, vp, vp, ci, ci, cd, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.srbd_mpc_solve_warm.argtypes = [vp, vp, vp, ci, ci, cd, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.srbd_mpc_solve_host.argtypes = [vp, vp, vp, ci, ci, ci, cd, vp, vp, vp]
     lib.srbd_qp_former_evaluate.restype = ctypes.c_float
     lib.srbd_qp_former_evaluate.argtypes = [vp, vp, vp, ci]
@@ -174,13 +175,24 @@ def qp_form(inputs: Sequence, out: Optional[List] = None) -> List:
 
 
 def marshal(f32_tensors: Sequence, mass: float, mu: float, fix_layout=False, q_stride_bug=False, out=None,
-            with_linearisation_point=True) -> List:
+            with_linearisation_point=True, i_body=None, rotation_body=None) -> List:
     """mpc_controller_cusadi.py:54-95 in one launch: 12 fp32 device tensors (x0, x_ref, R_body, I_world,
     root_position, foot_position, contact_table, dt_mpc, Q, R, residual_lin_accel, residual_ang_accel)
-    -> the 17 fp64 (B, nnz) qp_former inputs (entries 1, 2 are None unless with_linearisation_point)."""
+    -> the 17 fp64 (B, nnz) qp_former inputs (entries 1, 2 are None unless with_linearisation_point).
+    With i_body (3,3) and rotation_body (B,3,3) the kernel computes I_world = R I_body R' itself
+    (srbd_marshal_inputs_iw) and f32_tensors[3] may be None."""
     import torch
     lib = load()
     ts = []
+    on_device_iw = i_body is not None
+    if on_device_iw:
+        if rotation_body is None:
+            raise ValueError("marshal: i_body needs rotation_body")
+        for name, t, n in (("i_body", i_body, 9), ("rotation_body", rotation_body, None)):
+            if t.dtype != torch.float32 or t.device.type != "cuda" or not t.is_contiguous() or (n and t.numel() != n):
+                raise TypeError(f"marshal: {name} must be a contiguous float32 CUDA tensor" + (f" of {n} elements" if n else ""))
+        f32_tensors = list(f32_tensors)
+        f32_tensors[3] = rotation_body          # placeholder with the right shape for the checks below; not read
     for i, t in enumerate(f32_tensors):
         if t.dtype != torch.float32 or t.device.type != "cuda":
             raise TypeError(f"marshal: argument {i} must be a float32 CUDA tensor")
@@ -205,8 +217,15 @@ def marshal(f32_tensors: Sequence, mass: float, mu: float, fix_layout=False, q_s
         if any(out[i] is None for i in range(len(QP_NNZ_IN)) if i not in (1, 2)):
             raise ValueError("marshal out: only entries 1 and 2 (x, u) may be None")
     with torch.cuda.device(dev):
-        check(lib.srbd_marshal_inputs(_ptr_array(ts), int(ts[8].numel()), int(bool(fix_layout)), int(bool(q_stride_bug)),
-                                      float(mass), float(mu), _ptr_array(out, allow_none=True), B, _stream()))
+        if on_device_iw:
+            if rotation_body.numel() < B * 9 or rotation_body.device != dev or i_body.device != dev:
+                raise ValueError("marshal: rotation_body must hold B x 9 elements on the inputs' device")
+            check(lib.srbd_marshal_inputs_iw(_ptr_array(ts), ctypes.c_void_p(i_body.data_ptr()), ctypes.c_void_p(rotation_body.data_ptr()),
+                                             int(ts[8].numel()), int(bool(fix_layout)), int(bool(q_stride_bug)),
+                                             float(mass), float(mu), _ptr_array(out, allow_none=True), B, _stream()))
+        else:
+            check(lib.srbd_marshal_inputs(_ptr_array(ts), int(ts[8].numel()), int(bool(fix_layout)), int(bool(q_stride_bug)),
+                                          float(mass), float(mu), _ptr_array(out, allow_none=True), B, _stream()))
     return out
 
 
@@ -356,11 +375,14 @@ class Context:
                                      float(tol), ptr(w), *[ptr(t) for t in extra], ptr(iters_done), _stream()))
         return (w, *extra) if want_iterates else w
 
-    def solve_warm(self, inputs17, rotation_body, iters=20, tol=0.0, reset=None, want_iterates=False):
-        """EXTENSION (the reference cold-starts every tick): one tick warm-started from the (x, y) this
-        context found at its previous solve_warm call; s = max(h - G x, 1) and z = 1 are re-initialised.
+    def solve_warm(self, inputs17, rotation_body, iters=20, tol=0.0, reset=None, want_iterates=False, mode="xy"):
+        """EXTENSION (the reference cold-starts every tick): one tick warm-started from what this context found at
+        its previous solve_warm call.  mode "xy": (x, y) kept, s = max(h - G x, 1) and z = 1 re-initialised (20
+        iterations per tick).  mode "shift": (x, y, z) kept, shifted by one stage when the contact schedule rolled on,
+        s, z re-centred where the schedule changed (5-10 iterations per tick); see include/srbd_mpc.h.
         The first call is a cold start.  reset: optional int32 (B,) device tensor, nonzero = cold-start
         that env (episode reset).  inputs17[1] / [2] may be None.  Returns like solve()."""
+        mode_i = {"xy": 1, "shift": 2}[mode]
         import torch
         lib = load()
         ins, B, dev = _check_qp_inputs(inputs17)
@@ -372,7 +394,7 @@ class Context:
         ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
         x, s_, z, y, res = self._warm
         with torch.cuda.device(dev):
-            check(lib.srbd_mpc_solve_warm(self._h, _ptr_array(ins, allow_none=True), ptr(rot), B, int(iters), float(tol),
+            check(lib.srbd_mpc_solve_warm(self._h, _ptr_array(ins, allow_none=True), ptr(rot), B, int(iters), float(tol), mode_i,
                                           ptr(reset), ptr(w), ptr(x), ptr(s_), ptr(z), ptr(y), ptr(res), None, _stream()))
         return (w, x[:B], s_[:B], z[:B], y[:B], res[:B]) if want_iterates else w
 

@@ -134,6 +134,7 @@ struct srbd_ctx {
   cudaStream_t stream2 = nullptr;         // the two streams so that copies overlap the solve)
   cudaEvent_t done2 = nullptr;
   int have_prev = 0;                      // envs whose (x, y) of the previous srbd_mpc_solve_warm are in it[]
+  int have_sched = 0;                     // envs whose previous contact schedule is in work[] (any fused tick writes it)
   bool unfused = false;                   // SRBD_TICK_UNFUSED=1: assembly, solve and wrench as three launches
 };
 
@@ -255,7 +256,17 @@ int srbd_marshal_inputs(const float* const* f32in12, int nQ, int fix_layout, int
   for (int i = 0; i < 12; ++i) if (!f32in12[i]) return SRBD_EINVAL;
   for (int i = 0; i < QP_N_IN; ++i) if (!out17[i] && i != IN_X && i != IN_U) return SRBD_EINVAL;
   if (B == 0) return SRBD_OK;
-  SRBD_CUDA(launch_marshal(f32in12, nQ, fix_layout, q_stride_bug, mass, mu, out17, B, (cudaStream_t)stream));
+  SRBD_CUDA(launch_marshal(f32in12, nullptr, nullptr, nQ, fix_layout, q_stride_bug, mass, mu, out17, B, (cudaStream_t)stream));
+  return SRBD_OK;
+}
+
+int srbd_marshal_inputs_iw(const float* const* f32in12, const float* I_body, const float* rotation_body, int nQ, int fix_layout,
+                           int q_stride_bug, double mass, double mu, double* const* out17, int B, void* stream) {
+  if (!f32in12 || !out17 || !I_body || !rotation_body || B < 0 || nQ < 12) return SRBD_EINVAL;
+  for (int i = 0; i < 12; ++i) if (!f32in12[i] && i != 3) return SRBD_EINVAL;     // [3] (I_world) is computed, not read
+  for (int i = 0; i < QP_N_IN; ++i) if (!out17[i] && i != IN_X && i != IN_U) return SRBD_EINVAL;
+  if (B == 0) return SRBD_OK;
+  SRBD_CUDA(launch_marshal(f32in12, I_body, rotation_body, nQ, fix_layout, q_stride_bug, mass, mu, out17, B, (cudaStream_t)stream));
   return SRBD_OK;
 }
 
@@ -385,14 +396,14 @@ namespace {
 int solve_range(srbd_ctx* c, const double* const* in17, const float* rotation_body, int env0, int B,
                 int iters, double tol, float* wrench, double* x_out, double* s_out, double* z_out,
                 double* y_out, double* res_out, int* iters_done, cudaStream_t st,
-                bool warm = false, const int* reset = nullptr) {
+                int warm = 0, const int* reset = nullptr) {
   const size_t o = (size_t)env0;
   double* x = x_out ? x_out : c->it[0] + o * NZ;
   double* s = s_out ? s_out : c->it[1] + o * NINEQ;
   double* z = z_out ? z_out : c->it[2] + o * NINEQ;
   double* y = y_out ? y_out : c->it[3] + o * NEQ;
   double* res = res_out ? res_out : c->res + o * 4;
-  if (!c->unfused || warm) {
+  if (!c->unfused || warm != 0) {
     // ONE launch: the PDIPM kernel assembles its stage data from the 17 inputs (no CCS round trip
     // through HBM), iterates, and writes the wrench
     int rc = ensure_init();
@@ -407,7 +418,7 @@ int solve_range(srbd_ctx* c, const double* const* in17, const float* rotation_bo
     a.work = c->work + o * PDIPM_WORK_DOUBLES_FAST; a.work_stride = PDIPM_WORK_DOUBLES_FAST; a.inv_flag = nullptr;
     a.iters_done = iters_done; a.num_iters = iters; a.tol = tol;
     a.cold_start = 1; a.fused = 1; a.rot = rotation_body; a.wrench = wrench;
-    a.warm_xy = warm ? 1 : 0; a.reset = reset;
+    a.warm_xy = warm; a.reset = reset;
     SRBD_CUDA(launch_pdipm(a, B, true, num_sms(), st));
     return SRBD_OK;
   }
@@ -438,22 +449,30 @@ int srbd_mpc_solve(srbd_ctx* c, const double* const* in17, const float* rotation
   // the reference chains `num_calls` evaluations of a fixed-iteration kernel, feeding
   // (x,s,z,y) back (mpc_controller_cusadi.py:144-169); the iterate sequence is identical to
   // one call with num_calls*iters_per_call iterations, which is what is launched here.
-  return solve_range(c, in17, rotation_body, 0, B, num_calls * iters_per_call, tol, wrench, x_out, s_out, z_out,
-                     y_out, res_out, iters_done, (cudaStream_t)stream);
+  int rc = solve_range(c, in17, rotation_body, 0, B, num_calls * iters_per_call, tol, wrench, x_out, s_out, z_out,
+                       y_out, res_out, iters_done, (cudaStream_t)stream);
+  if (rc == SRBD_OK && !c->unfused && B > c->have_sched) c->have_sched = B;
+  return rc;
 }
 
 int srbd_mpc_solve_warm(srbd_ctx* c, const double* const* in17, const float* rotation_body, int B,
-                        int iters, double tol, const int* reset, float* wrench, double* x_io, double* s_out,
-                        double* z_out, double* y_io, double* res_out, int* iters_done, void* stream) {
+                        int iters, double tol, int mode, const int* reset, float* wrench, double* x_io, double* s_out,
+                        double* z_io, double* y_io, double* res_out, int* iters_done, void* stream) {
   if (!c || !in17 || B < 0 || B > c->max_B || iters < 0) return SRBD_EINVAL;
+  if (mode != SRBD_WARM_XY && mode != SRBD_WARM_SHIFT) return SRBD_EINVAL;
   if (wrench && !rotation_body) return SRBD_EINVAL;
   if ((x_io == nullptr) != (y_io == nullptr)) return SRBD_EINVAL;
+  if (mode == SRBD_WARM_SHIFT && x_io && !z_io) return SRBD_EINVAL;     // the multipliers are carried over too
   if (B == 0) return SRBD_OK;
-  // with the context's own buffers the first call has nothing to start from: it is a cold start
-  const bool warm = (x_io != nullptr) || c->have_prev >= B;
-  int rc = solve_range(c, in17, rotation_body, 0, B, iters, tol, wrench, x_io, s_out, z_out, y_io, res_out, iters_done,
-                       (cudaStream_t)stream, warm, warm ? reset : nullptr);
+  // with the context's own buffers the first call has nothing to start from: it is a cold start.  The shifted mode
+  // also needs the previous tick's contact schedule, which lives in the context's work buffer: the context must have
+  // solved (cold or warm) at least B envs before.
+  bool warm = (x_io != nullptr) || c->have_prev >= B;
+  if (mode == SRBD_WARM_SHIFT && c->have_sched < B) warm = false;
+  int rc = solve_range(c, in17, rotation_body, 0, B, iters, tol, wrench, x_io, s_out, z_io, y_io, res_out, iters_done,
+                       (cudaStream_t)stream, warm ? mode : 0, warm ? reset : nullptr);
   if (rc == SRBD_OK && !x_io) c->have_prev = B;
+  if (rc == SRBD_OK && B > c->have_sched) c->have_sched = B;
   return rc;
 }
 

@@ -27,9 +27,11 @@ struct PdipmArgs {
   //      the CCS vectors in[0..5], and turn u0 into the body-frame wrench at the end
   int fused;                    // 1: qp_in[] is used, in[0..5] are ignored
   const double* qp_in[QP_N_IN]; // qp_former inputs (x, u may be null = ones)
-  int warm_xy;                  // with cold_start: keep (x, y) found in out[] (the previous tick's solution) and
-                                //   re-initialise only s = max(h - G x, 1), z = 1 -- an extension; the reference
-                                //   cold-starts every tick (mpc_controller_cusadi.py:138-141)
+  int warm_xy;                  // with cold_start, an extension (the reference cold-starts every tick,
+                                //   mpc_controller_cusadi.py:138-141).  1: keep (x, y) found in out[] (the previous tick's
+                                //   solution), re-initialise s = max(h - G x, 1), z = 1.  2 (fused tick): keep (x, y, z),
+                                //   shifted by one stage when the contact schedule rolled on; s = max(h - G x, 1e-2); z
+                                //   floored at 1e-3, re-centred (z = 0.1 / s) on the rows whose bound the schedule changed
   const int* reset;             // optional (B): envs with reset[e] != 0 are cold-started although warm_xy is set
   const float* rot;             // optional (B,3,3) fp32 row-major state-estimate rotation
   float* wrench;                // optional (B,2,6) fp32 (mpc_controller_cusadi.py:186-203)

@@ -23,8 +23,8 @@ cudaError_t launch_wrench(const double* x_sol, const float* rotation_body_rowmaj
 cudaError_t launch_stage_invariant_probe(const double* Q, const double* G, const double* A, int* flag, int B,
                                          cudaStream_t stream);
 // controller state (fp32) -> the qp_former inputs (fp64), mpc_controller_cusadi.py:54-95
-cudaError_t launch_marshal(const float* const* f32in12, int nQ, int fix_layout, int q_stride_bug, double mass, double mu,
-                           double* const* out17, int B, cudaStream_t stream);
+cudaError_t launch_marshal(const float* const* f32in12, const float* I_body, const float* rotation_body, int nQ, int fix_layout,
+                           int q_stride_bug, double mass, double mu, double* const* out17, int B, cudaStream_t stream);
 // estimator state + command (fp32) -> x0, x_ref and the open-loop knot point, base_controller.py:164-257
 cudaError_t launch_reference_trajectory(const float* const* f32in9, float step, float* wpd, float* yaw_des,
                                         unsigned char* first_run, float* x0, float* x_ref, int B, cudaStream_t stream);

@@ -66,6 +66,7 @@ cudaError_t launch_stage_invariant_probe(const double* Q, const double* G, const
 // reproduces the 13-long Q strided by 12 (Q3).
 struct MarshalArgs {
   const float *x0, *x_ref, *R_body, *I_world, *root_pos, *foot_pos, *contact, *dt_mpc, *Q, *R, *res_lin, *res_ang;
+  const float *I_body, *rot;   // non-null: I_world = rot I_body rot' is computed here (mpc_controller_cusadi.py:60-63), I_world is ignored
   int nQ, fix_layout, q_stride_bug;
   double mass, mu;
   double* out[QP_N_IN];   // out[IN_X] / out[IN_U] may be null (not written: the kernels treat null as ones)
@@ -88,7 +89,21 @@ __global__ void marshal_kernel(MarshalArgs a, int B) {
   if (lane < 9) {   // flat[k]: fix_layout ? column-major nnz order of the true matrix : row-major as is
     const int src = a.fix_layout ? (lane % 3) * 3 + lane / 3 : lane;
     a.out[IN_RBODY][e * 9 + lane] = (double)a.R_body[e * 9 + src];
-    a.out[IN_IWORLD][e * 9 + lane] = (double)a.I_world[e * 9 + src];
+    float iw;
+    if (a.I_body) {   // entry (i, j) of R I_body R' in fp32, two chained matrix products like the reference's `R @ I_body @ R.T`
+      const int i = src / 3, j = src - 3 * i;
+      const float* Rm = a.rot + e * 9;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float t = fmaf(Rm[3 * i + 2], a.I_body[6 + k], fmaf(Rm[3 * i + 1], a.I_body[3 + k], Rm[3 * i] * a.I_body[k]));   // (R I_body)[i][k]
+        acc = (k == 0) ? t * Rm[3 * j] : fmaf(t, Rm[3 * j + k], acc);
+      }
+      iw = acc;
+    } else {
+      iw = a.I_world[e * 9 + src];
+    }
+    a.out[IN_IWORLD][e * 9 + lane] = (double)iw;
   }
   if (lane < 20) {  // contact (10,2) row-major; fix_layout: flat[k] = contact[k % 10, k / 10]
     const int src = a.fix_layout ? (lane % 10) * 2 + lane / 10 : lane;
@@ -108,13 +123,14 @@ __global__ void marshal_kernel(MarshalArgs a, int B) {
   }
 }
 
-cudaError_t launch_marshal(const float* const* f32in12, int nQ, int fix_layout, int q_stride_bug, double mass, double mu,
-                           double* const* out17, int B, cudaStream_t stream) {
+cudaError_t launch_marshal(const float* const* f32in12, const float* I_body, const float* rotation_body, int nQ, int fix_layout,
+                           int q_stride_bug, double mass, double mu, double* const* out17, int B, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
   MarshalArgs a;
   a.x0 = f32in12[0]; a.x_ref = f32in12[1]; a.R_body = f32in12[2]; a.I_world = f32in12[3]; a.root_pos = f32in12[4];
   a.foot_pos = f32in12[5]; a.contact = f32in12[6]; a.dt_mpc = f32in12[7]; a.Q = f32in12[8]; a.R = f32in12[9];
   a.res_lin = f32in12[10]; a.res_ang = f32in12[11];
+  a.I_body = I_body; a.rot = rotation_body;
   a.nQ = nQ; a.fix_layout = fix_layout; a.q_stride_bug = q_stride_bug; a.mass = mass; a.mu = mu;
   for (int i = 0; i < QP_N_IN; ++i) a.out[i] = out17[i];
   marshal_kernel<<<(B + 3) / 4, 128, 0, stream>>>(a, B);

@@ -596,6 +596,10 @@ struct PdipmFast {
     for (int m = 16; m >= 1; m >>= 1) { const double o = w.shfl_xor(v, m); v = o < v ? o : v; }
     return v;
   }
+  // stage-shifted warm start (warm_xy == 2): floor of the re-initialised slacks, floor of the carried multipliers and
+  // the complementarity product rows are re-centred to where the contact schedule changed their bound -- tuned on the
+  // closed-loop rollouts of tests/closed_loop.py with the oracle
+  static constexpr double WARM_S_MIN = 1e-2, WARM_Z_MIN = 1e-3, WARM_MU0 = 0.1;
   SRBD_DEV static double ratio(double v, double dv) { return dv < 0.0 ? -v * rcp(dv) : 1.0; }
   SRBD_DEV static double step_len(double mn) { return fmax(fmin(1.0, 0.99 * mn), 1e-12); }
 
@@ -607,13 +611,20 @@ struct PdipmFast {
     lane = w.lane(); h = lane >> 4; r = lane & 15; rr = r < 12 ? r : 11;
     {
       double* oX = gout(IPO_X, NZ); double* oS = gout(IPO_S, NINEQ); double* oZ = gout(IPO_Z, NINEQ); double* oY = gout(IPO_Y, NEQ);
-      const bool keep_xy = A.cold_start && A.warm_xy && !(A.reset && A.reset[e] != 0);
+      const bool warm = A.cold_start && A.warm_xy && !(A.reset && A.reset[e] != 0);
+      const bool keep_xy = warm;
+      // warm_xy == 2 (fused tick only): (x, y, z) of the previous tick are kept -- shifted by one stage when the contact
+      // schedule has rolled on -- and s, z are re-centred where the schedule changed (below).  The previous tick's
+      // F_max * contact row is still in the work buffer: read it before the set-up overwrites it.
+      const bool shifted = warm && A.warm_xy == 2 && A.fused;
+      double fc_old = 0.0;
+      if (shifted && lane < 20) fc_old = gws()[FW_FC + lane];
       if (A.cold_start) {
         if (!keep_xy) {
           for (int i = lane; i < NZ; i += 32) oX[i] = 0.0;
           for (int i = lane; i < NEQ; i += 32) oY[i] = 1.0;
         }
-        for (int i = lane; i < NINEQ; i += 32) oZ[i] = 1.0;
+        if (!shifted) for (int i = lane; i < NINEQ; i += 32) oZ[i] = 1.0;
       } else {
         const double* ix = gin(IP_X, NZ); const double* is = gin(IP_S, NINEQ);
         const double* iz = gin(IP_Z, NINEQ); const double* iy = gin(IP_Y, NEQ);
@@ -633,7 +644,51 @@ struct PdipmFast {
         }
         return -1;
       }
-      if (A.cold_start) {   // s = max(h - G x, 1) (x = 0 unless warm); in fused mode h only exists after the set-up
+      if (shifted) {
+        // ---- one-stage shift when the contact schedule rolled (stage k now is what stage k + 1 was) ---------------
+        const double fc_new = lane < 20 ? gws()[FW_FC + lane] : 0.0;
+        const bool rolled = w.any(lane < 20 && fc_new != fc_old);
+        if (rolled) {
+          double xv[8], yv[5], zv[5];
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {   // x: states 0..119 and inputs 120..239, twelve per stage
+            const int i = lane + 32 * m;
+            const int src = (i < NZ && (i % 120) < 108) ? i + 12 : i;
+            xv[m] = i < NZ ? oX[src] : 0.0;
+          }
+#pragma unroll
+          for (int m = 0; m < 5; ++m) {   // y: dynamics rows 0..119 (twelve per stage), Mx rows 120..139 (two per stage); z: sixteen
+            const int i = lane + 32 * m;
+            const int ys = i < 108 ? i + 12 : ((i >= 120 && i < 138) ? i + 2 : i);
+            yv[m] = i < NEQ ? oY[ys] : 0.0;
+            const int zs = i < 144 ? i + 16 : i;
+            zv[m] = oZ[zs];
+          }
+          w.sync();
+#pragma unroll
+          for (int m = 0; m < 8; ++m) { const int i = lane + 32 * m; if (i < NZ) oX[i] = xv[m]; }
+#pragma unroll
+          for (int m = 0; m < 5; ++m) { const int i = lane + 32 * m; if (i < NEQ) oY[i] = yv[m]; oZ[i] = zv[m]; }
+          const double nxt = w.shfl(fc_old, lane + 2 < 20 ? lane + 2 : lane);
+          fc_old = nxt;
+          w.sync();
+        }
+        // ---- s = max(h - G x, s_min); z kept (floored) where the row's bound is unchanged, re-centred (z = mu0 / s)
+        //      where the schedule changed it (rows 7 / 15 of a stage: fz <= F_max * contact) -----------------------
+        const double* f = fb();
+        const double ga = f[goa], gb = f[gob];
+        const int q7 = (r & 7) == 7;
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+          const int k = h ? 9 - t : t, j = 16 * k + r;
+          const double gx = ga * oX[120 + 12 * k + ca] + gb * oX[120 + 12 * k + cz];
+          const double sv = fmax(h_of(k, j) - gx, WARM_S_MIN);
+          const double fo = w.shfl(fc_old, 2 * k + ((r >> 3) & 1));
+          const bool changed = q7 && fo != gws()[FW_FC + 2 * k + ((r >> 3) & 1)];
+          oS[j] = sv;
+          oZ[j] = changed ? WARM_MU0 * rcp(sv) : fmax(oZ[j], WARM_Z_MIN);
+        }
+      } else if (A.cold_start) {   // s = max(h - G x, 1) (x = 0 unless warm); in fused mode h only exists after the set-up
         const double* f = fb();
         const double ga = f[goa], gb = f[gob];
 #pragma unroll

@@ -27,22 +27,29 @@ from typing import Tuple
 from . import _native
 
 
-def marshal_inputs(ctrl, fix_layout: bool = False, reproduce_q_stride_bug: bool = False, with_linearisation_point=True):
+def marshal_inputs(ctrl, fix_layout: bool = False, reproduce_q_stride_bug: bool = False, with_linearisation_point=True,
+                   torch_i_world: bool = False):
     """The 17 fp64 (B, nnz) tensors of mpc_controller_cusadi.py:77-95 from controller state, built by ONE
-    kernel (srbd_marshal_inputs) instead of ~25 small torch ops; `marshal_inputs_torch` is the literal
-    torch restatement the tests compare it with.  Only I_world = R I_body R' is still computed by torch
-    (fp32 batched matmul, like the reference: its rounding cannot be reproduced elsewhere)."""
+    kernel (srbd_marshal_inputs_iw) instead of ~25 small torch ops; `marshal_inputs_torch` is the literal
+    torch restatement the tests compare it with.  I_world = R I_body R' (:60-63) is computed inside the same launch
+    (fp32, within 2 ulp of torch's two batched matmuls); torch_i_world=True computes it with torch like the reference and
+    passes it in, which reproduces the reference's own rounding on the same back-end."""
     import torch
     sed = ctrl.state_estimate_data
     rot = sed.rotation_body
-    I_w = rot @ ctrl.biped.I_body.unsqueeze(0) @ rot.transpose(1, 2)
     f32 = lambda t: torch.as_tensor(t, dtype=torch.float32, device=ctrl.device)
+    iw_args = {}
+    if torch_i_world:
+        I_w = rot @ ctrl.biped.I_body.unsqueeze(0) @ rot.transpose(1, 2)
+    else:
+        I_w = None
+        iw_args = dict(i_body=f32(ctrl.biped.I_body).contiguous(), rotation_body=f32(rot).contiguous())
     return _native.marshal(
         [f32(ctrl.x0), f32(ctrl.x_ref), f32(ctrl.R_body[:, 0, :, :]), I_w, f32(sed.root_position), f32(sed.foot_position),
          f32(ctrl.contact_table), f32(ctrl.dt_mpc), f32(ctrl.Q), f32(ctrl.R), f32(ctrl.residual_lin_accel),
          f32(ctrl.residual_ang_accel)],
         float(ctrl.mass), float(ctrl.mu), fix_layout, reproduce_q_stride_bug and ctrl.Q.numel() != 12,
-        with_linearisation_point=with_linearisation_point)
+        with_linearisation_point=with_linearisation_point, **iw_args)
 
 
 def marshal_inputs_torch(ctrl, fix_layout: bool = False, reproduce_q_stride_bug: bool = False):

@@ -126,6 +126,13 @@ int srbd_pdipm_is_stage_invariant(const double* const* in10, int B, void* stream
  * Q1, Q2), 1 passes the intended layout; q_stride_bug = 1 reproduces the 13-long Q strided by 12 (Q3). */
 int srbd_marshal_inputs(const float* const* f32in12, int nQ, int fix_layout, int q_stride_bug, double mass, double mu,
                         double* const* out17, int B, void* stream);
+/* The same with I_world = R I_body R' (mpc_controller_cusadi.py:60-63: two fp32 batched matmuls per tick in the reference)
+ * computed inside the launch: I_body = device fp32 (3,3) row-major shared by all envs, rotation_body = device fp32
+ * (B,3,3) row-major (state_estimate_data.rotation_body); f32in12[3] is ignored and may be NULL.  fp32 fused multiply-adds
+ * in the order of two chained 3x3 products: within 2 ulp of torch's `R @ I_body @ R.T`.  With this entry the MPC tick
+ * is three launches (state builder, input builder, fused solve) and no torch op. */
+int srbd_marshal_inputs_iw(const float* const* f32in12, const float* I_body, const float* rotation_body, int nQ, int fix_layout,
+                           int q_stride_bug, double mass, double mu, double* const* out17, int B, void* stream);
 
 /* ---- the control step around the MPC tick (HECTOR biped), SURVEY 8f rank 3 ------------------------ *
  * Device buffers of one batch of B envs; all fp32 unless noted, shapes in the comments.  The names are     *
@@ -228,16 +235,24 @@ int srbd_mpc_solve(srbd_ctx* ctx, const double* const* in17, const float* rotati
                    int num_calls, int iters_per_call, double tol,
                    float* wrench, double* x_out, double* s_out, double* z_out, double* y_out,
                    double* res_out, int* iters_done, void* stream);
-/* EXTENSION (not in the reference, which cold-starts every tick): the same tick warm-started from the
- * previous tick's primal / equality-dual solution.  (x, y) are kept, s = max(h - G x, 1) and z = 1
- * are re-initialised as in the cold start; in the closed-loop rollouts of tests/closed_loop.py 20
- * warm iterations per tick do what 30 cold ones do.  x_io / y_io: device buffers holding the previous
- * solution on entry and the new one on return, or both NULL = the context's own buffers (whose first
- * call is then a cold start).  reset: optional device int[B]; envs with reset[e] != 0 (episode
- * resets) are cold-started.  `iters` Newton iterations in one launch. */
+/* EXTENSION (not in the reference, which cold-starts every tick, mpc_controller_cusadi.py:138-141): the same tick
+ * warm-started from the previous tick's solution, `iters` Newton iterations in one launch.
+ *   mode = SRBD_WARM_XY     (x, y) are kept, s = max(h - G x, 1) and z = 1 are re-initialised as in the cold start;
+ *                           20 warm iterations per tick do what 30 cold ones do in tests/closed_loop.py.
+ *   mode = SRBD_WARM_SHIFT  (x, y, z) are kept and, when the contact schedule of the tick differs from the previous
+ *                           tick's (the horizon rolled on by one stage), shifted by one stage; s = max(h - G x, 1e-2);
+ *                           z is floored at 1e-3 and re-centred (z = 0.1 / s) on the rows whose bound the schedule
+ *                           changed (contact switches).  5-10 warm iterations per tick do what 30 cold ones do.  The
+ *                           previous schedule is remembered in the context's workspace: use one context per batch
+ *                           and keep the env order.
+ * x_io / y_io (/ z_io): device buffers holding the previous solution on entry and the new one on return, or all NULL =
+ * the context's own buffers (whose first call is then a cold start).  reset: optional device int[B]; envs with
+ * reset[e] != 0 (episode resets) are cold-started. */
+#define SRBD_WARM_XY 1
+#define SRBD_WARM_SHIFT 2
 int srbd_mpc_solve_warm(srbd_ctx* ctx, const double* const* in17, const float* rotation_body, int B,
-                        int iters, double tol, const int* reset, float* wrench, double* x_io, double* s_out,
-                        double* z_out, double* y_io, double* res_out, int* iters_done, void* stream);
+                        int iters, double tol, int mode, const int* reset, float* wrench, double* x_io, double* s_out,
+                        double* z_io, double* y_io, double* res_out, int* iters_done, void* stream);
 /* the same with HOST buffers, synchronous.  Page-locked (pinned) buffers are read and written over PCIe by
  * the kernels themselves (UVA mapping); pageable ones are staged with cudaMemcpyAsync.  The batch is cut into
  * chunks that alternate between two internal streams; a prefetch kernel that co-resides with the running

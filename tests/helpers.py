@@ -95,18 +95,27 @@ def emul_pdipm(qp, iters, x=None, s=None, z=None, y=None, tol=0.0, uniform=True,
     return outs, itd
 
 
-def emul_tick(inputs17, rot, iters, tol=0.0, lane_order=1, pair=False, warm_from=None, reset=None):
+def emul_tick(inputs17, rot, iters, tol=0.0, lane_order=1, pair=False, warm_from=None, reset=None, work=None):
     """The fused tick (assembly from the 17 qp_former inputs + PDIPM + wrench) of the fast kernel under
-    the CPU warp emulator.  inputs17[1] / [2] may be None.  Returns (outs6, wrench (B,2,6) fp32)."""
+    the CPU warp emulator.  inputs17[1] / [2] may be None.  Returns (outs6, wrench (B,2,6) fp32).
+    warm_from = (x, y): warm mode 1; (x, y, z): warm mode 2 (stage-shifted; `work` must then be the array a previous
+    call used, which holds that tick's contact schedule)."""
     lib = emul_lib()
     B = inputs17[0].shape[0]
     ins = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in inputs17]
     rot32 = np.ascontiguousarray(rot, dtype=np.float32)
     outs = [np.zeros((B, n)) for n in (240, 160, 160, 140, 4, 1)]
-    if warm_from is not None:                 # (x, y) of the previous tick, found in the output buffers
+    mode = 0
+    if warm_from is not None:                 # the previous tick's solution, found in the output buffers
         outs[0][:] = warm_from[0]; outs[3][:] = warm_from[1]
+        mode = 1
+        if len(warm_from) == 3:
+            outs[2][:] = warm_from[2]
+            mode = 2
     rst = None if reset is None else np.ascontiguousarray(reset, dtype=np.int32)
-    work = np.zeros((B, bp._native.WORK_DOUBLES))
+    if work is None:
+        work = np.zeros((B, bp._native.WORK_DOUBLES))
+    assert work.shape == (B, bp._native.WORK_DOUBLES) and work.flags.c_contiguous
     wrench = np.zeros((B, 2, 6), np.float32)
     itd = np.zeros(B, np.int32)
     P = ctypes.POINTER(ctypes.c_double)
@@ -115,7 +124,7 @@ def emul_tick(inputs17, rot, iters, tol=0.0, lane_order=1, pair=False, warm_from
     lib.srbd_emul_set_order(int(lane_order))
     lib.srbd_emul_tick(inarr, rot32.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), outarr, work.ctypes.data_as(P),
                        wrench.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), itd.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
-                       B, int(iters), ctypes.c_double(tol), int(pair), int(warm_from is not None),
+                       B, int(iters), ctypes.c_double(tol), int(pair), int(mode),
                        rst.ctypes.data_as(ctypes.POINTER(ctypes.c_int)) if rst is not None else None)
     lib.srbd_emul_set_order(1)
     return outs, wrench

@@ -68,7 +68,7 @@ def test_error_paths_do_not_exit():
     assert lib.srbd_pdipm_is_stage_invariant(None, 4, None, ctypes.byref(res)) == -1
     assert lib.srbd_marshal_inputs(None, 13, 0, 0, 40.0, 1.0, None, 4, None) == -1
     assert lib.srbd_mpc_solve(None, None, None, 4, 4, 5, 0.0, None, None, None, None, None, None, None, None) == -1
-    assert lib.srbd_mpc_solve_warm(None, None, None, 4, 20, 0.0, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.srbd_mpc_solve_warm(None, None, None, 4, 20, 0.0, 2, None, None, None, None, None, None, None, None, None) == -1
     assert lib.srbd_mpc_solve_host(None, None, None, 4, 4, 5, 0.0, None, None, None) == -1
     assert lib.srbd_wrench(None, None, None, 4, None) == -1
     assert lib.srbd_reference_trajectory(None, 0.01, None, None, None, None, None, 4, None) == -1

@@ -126,3 +126,63 @@ def test_warm_start_semantics():
     for i in range(4):
         assert np.array_equal(warm[i][1], cold[i][1])
         assert rel_err(warm[i][[0, 2]], ref[i][[0, 2]]) < 1e-10
+
+
+def test_shifted_warm_start_semantics_and_closed_loop():
+    """warm mode 2 (SRBD_WARM_SHIFT): (x, y, z) kept; shifted by one stage when the contact schedule differs from the
+    previous tick's; s = max(h - G x, 1e-2); z floored at 1e-3 and re-centred (0.1 / s) on the rows whose bound changed.
+    (i) the start point the device code builds equals the numpy restatement (compared after 0 iterations), with and
+    without a roll of the schedule; (ii) 6 warm iterations per tick keep a small walking batch on its feet for 1.5 s,
+    which 6 cold iterations do not."""
+    import closed_loop as cl
+    from oracle import srbd_oracle as so
+    B = 3
+    ro = cl.Rollout(B, seed=4, walking=True)
+    ro.phase[:] = [0.01, 0.0999, 0.35]        # env 1 rolls to the next stage at the next tick (phase step 0.04 per tick)
+    rot = np.repeat(np.eye(3)[None], B, 0)
+    ins0, c0 = ro.inputs()
+    work = np.zeros((B, bp._native.WORK_DOUBLES))
+    cold, _ = emul_tick(ins0, rot, 8, work=work)
+    ro.plant_steps(cold[0][:, 120:132], c0); ro.advance_gait_and_feet(c0)
+    ins1, _ = ro.inputs()
+    qp0, qp1 = oracle_qp_batch(ins0), oracle_qp_batch(ins1)
+    rolled = np.any(qp0[5] != qp1[5], axis=1)
+    assert rolled.tolist() == [False, True, False]
+    start, _ = emul_tick(ins1, rot, 0, warm_from=(cold[0], cold[3], cold[2]), work=work.copy())
+
+    def sh(v, n, idx):
+        w = v.reshape(B, 10, n).copy()
+        w[idx] = np.concatenate([w[idx, 1:], w[idx, -1:]], 1)
+        return w.reshape(B, -1)
+    x = np.concatenate([sh(cold[0][:, :120], 12, rolled), sh(cold[0][:, 120:], 12, rolled)], 1)
+    y = np.concatenate([sh(cold[3][:, :120], 12, rolled), sh(cold[3][:, 120:], 2, rolled)], 1)
+    z = sh(cold[2], 16, rolled)
+    d_old = sh(qp0[5], 16, rolled)
+    Gx = np.stack([so.dense_from_ccs(qp1[4][e], so.G_COLPTR, so.G_ROW, (160, 240)) @ x[e] for e in range(B)])
+    s_ref = np.maximum(qp1[5] - Gx, 1e-2)
+    z_ref = np.where(d_old != qp1[5], 0.1 / s_ref, np.maximum(z, 1e-3))
+    assert np.array_equal(start[0], x) and np.array_equal(start[3], y)
+    assert np.allclose(start[1], s_ref, rtol=1e-14, atol=0) and np.allclose(start[2], z_ref, rtol=1e-14, atol=0)
+    # reset mask: those envs are cold-started, bit for bit
+    r_cold, _ = emul_tick(ins1, rot, 5, work=work.copy())
+    r_mix, _ = emul_tick(ins1, rot, 5, warm_from=(cold[0], cold[3], cold[2]), reset=[0, 1, 0], work=work.copy())
+    for i in range(4):
+        assert np.array_equal(r_mix[i][1], r_cold[i][1]) and not np.array_equal(r_mix[i][0], r_cold[i][0])
+
+    # (ii) closed loop, 150 ticks = 1.5 s of walking
+    def rollout(warm, iters, ticks=150):
+        r = cl.Rollout(4, seed=11, walking=True)
+        rot4 = np.repeat(np.eye(3)[None], 4, 0)
+        wk = np.zeros((4, bp._native.WORK_DOUBLES))
+        prev = [None]
+
+        def solve(ins):
+            out, _ = emul_tick(ins, rot4, iters, warm_from=prev[0] if warm else None, work=wk)
+            prev[0] = (out[0], out[3], out[2])
+            return out[0]
+        r.run(solve, ticks)
+        return r.summary()
+    w6 = rollout(True, 6)
+    assert w6["finite"] and w6["height_err_max"] < 0.05 and w6["tilt_max"] < 0.05, w6
+    c6 = rollout(False, 6, ticks=60)
+    assert (not c6["finite"]) or c6["height_err_max"] > w6["height_err_max"], (c6, w6)

@@ -380,7 +380,14 @@ def test_input_builder_kernel_equals_torch_marshalling(fix_layout, qbug):
     b = bp.mpc_controller_b200.marshal_inputs_torch(c, fix_layout, qbug)
     for i, (u, v) in enumerate(zip(a, b)):
         assert u.dtype == torch.float64 and tuple(u.shape) == (37, bp._native.QP_NNZ_IN[i])
-        assert torch.equal(u, v.reshape(37, -1)), i
+        if i == 8:      # I_world = R I_body R' computed inside the launch: fp32, within 2 ulp of torch's two matmuls
+            ulp = torch.finfo(torch.float32).eps * v.reshape(37, -1).abs().amax(dim=1, keepdim=True)
+            assert ((u - v.reshape(37, -1)).abs() <= 2.0 * ulp).all()
+            assert torch.equal(u, u.float().double())                       # still fp32 values
+        else:
+            assert torch.equal(u, v.reshape(37, -1)), i
+    t = bp.mpc_controller_b200.marshal_inputs(c, fix_layout, qbug, torch_i_world=True)   # torch's I_world passed in: bit for bit
+    assert all(torch.equal(u, v.reshape(37, -1)) for u, v in zip(t, b))
     nox = bp.mpc_controller_b200.marshal_inputs(c, fix_layout, qbug, with_linearisation_point=False)
     assert nox[1] is None and nox[2] is None and torch.equal(nox[3], a[3])
 
