@@ -18,7 +18,7 @@ COMPAT_LIBS = {
     "libqp_former.so": "qp_former_evaluate.c",
     "libsparse_pdipm_multiple_iterations.so": "sparse_pdipm_evaluate.c",
 }
-CU_SOURCES = ("srbd_abi.cu", "srbd_qp_form.cu", "srbd_pdipm.cu", "srbd_misc.cu", "srbd_lowlevel.cu")
+CU_SOURCES = ("srbd_abi.cu", "srbd_qp_form.cu", "srbd_pdipm.cu", "srbd_misc.cu", "srbd_lowlevel.cu", "srbd_t1.cu")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas=-v"]
 

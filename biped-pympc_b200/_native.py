@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "srbd_pattern", "srbd_loop_buffers_size", "srbd_update_state", "srbd_lowlevel", "srbd_gait", "srbd_reference_trajectory", "srbd_marshal_inputs", "srbd_marshal_inputs_iw", "srbd_qp_form", "srbd_pdipm_work_doubles", "srbd_pdipm", "srbd_pdipm_is_stage_invariant", "srbd_wrench",
     "srbd_ctx_create", "srbd_ctx_destroy", "srbd_mpc_solve", "srbd_mpc_solve_warm", "srbd_mpc_solve_host",
     "srbd_qp_former_evaluate", "srbd_sparse_pdipm_multiple_iterations_evaluate", "srbd_dfma_peak",
+    "srbd_t1_kinematics", "srbd_t1_inverse_kinematics",
 )
 
 
@@ -80,6 +81,8 @@ def load(build_if_missing: bool = True):
     lib.srbd_sparse_pdipm_multiple_iterations_evaluate.restype = ctypes.c_float
     lib.srbd_sparse_pdipm_multiple_iterations_evaluate.argtypes = [vp, vp, vp, ci]
     lib.srbd_dfma_peak.argtypes = [ci, ci, ci, ctypes.POINTER(cd)]
+    lib.srbd_t1_kinematics.argtypes = [vp, vp, vp, ci, vp]
+    lib.srbd_t1_inverse_kinematics.argtypes = [vp, vp, ci, vp]
     _lib = lib
     return lib
 
@@ -426,6 +429,37 @@ class Context:
                                       int(num_calls), int(iters_per_call), float(tol), ptr(wrench_host),
                                       ptr(x_out_host), ptr(res_out_host)))
         return wrench_host
+
+
+def t1_kinematics(joint_angle, want_jacobian=True):
+    """Batched T1 forward kinematics (+ contact Jacobian): joint_angle (B,2,6) fp32 CUDA -> (foot_position (B,2,3),
+    jacobian (B,2,6,6) or None).  Replaces core/robot/t1.py:96-138 (CasADi on the CPU, env 0 only)."""
+    import torch
+    lib = load()
+    if joint_angle.dtype != torch.float32 or joint_angle.device.type != "cuda" or joint_angle.shape[-2:] != (2, 6):
+        raise TypeError("t1_kinematics: joint_angle must be a float32 CUDA tensor of shape (B, 2, 6)")
+    q = joint_angle.contiguous()
+    B, dev = q.shape[0], q.device
+    p = torch.empty((B, 2, 3), dtype=torch.float32, device=dev)
+    J = torch.empty((B, 2, 6, 6), dtype=torch.float32, device=dev) if want_jacobian else None
+    with torch.cuda.device(dev):
+        check(lib.srbd_t1_kinematics(ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(p.data_ptr()),
+                                     ctypes.c_void_p(J.data_ptr()) if J is not None else None, B, _stream()))
+    return p, J
+
+
+def t1_inverse_kinematics(foot_position):
+    """T1.analytical_IK (t1.py:139-213) for both legs of every env: (B,2,3) fp32 CUDA -> (B,2,6)."""
+    import torch
+    lib = load()
+    if foot_position.dtype != torch.float32 or foot_position.device.type != "cuda" or foot_position.shape[-2:] != (2, 3):
+        raise TypeError("t1_inverse_kinematics: foot_position must be a float32 CUDA tensor of shape (B, 2, 3)")
+    p = foot_position.contiguous()
+    B, dev = p.shape[0], p.device
+    q = torch.empty((B, 2, 6), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.srbd_t1_inverse_kinematics(ctypes.c_void_p(p.data_ptr()), ctypes.c_void_p(q.data_ptr()), B, _stream()))
+    return q
 
 
 def dfma_peak(iters=20000, blocks=148 * 8, threads=256) -> float:

@@ -335,6 +335,20 @@ int srbd_lowlevel(const srbd_loop_buffers* buf, const float* kp, const float* kd
   return SRBD_OK;
 }
 
+int srbd_t1_kinematics(const float* joint_angle, float* foot_position, float* jacobian, int B, void* stream) {
+  if (B == 0) return SRBD_OK;
+  if (!joint_angle || (!foot_position && !jacobian) || B < 0) return SRBD_EINVAL;
+  SRBD_CUDA(launch_t1_kinematics(joint_angle, foot_position, jacobian, B, (cudaStream_t)stream));
+  return SRBD_OK;
+}
+
+int srbd_t1_inverse_kinematics(const float* foot_position, float* joint_angle, int B, void* stream) {
+  if (B == 0) return SRBD_OK;
+  if (!foot_position || !joint_angle || B < 0) return SRBD_EINVAL;
+  SRBD_CUDA(launch_t1_ik(foot_position, joint_angle, B, (cudaStream_t)stream));
+  return SRBD_OK;
+}
+
 int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, int B, void* stream) {
   if (B == 0) return SRBD_OK;
   if (!x_sol || !rotation_body || !wrench || B < 0) return SRBD_EINVAL;

@@ -37,6 +37,9 @@ struct UpdateStateArgs;
 struct LowLevelArgs;
 cudaError_t launch_update_state(const UpdateStateArgs& a, int B, cudaStream_t stream);
 cudaError_t launch_lowlevel(const LowLevelArgs& a, int B, cudaStream_t stream);
+// T1 biped: sole position (B,2,3) and contact Jacobian (B,2,6,6) from the joint angles (B,2,6); analytical IK (srbd_t1.cu)
+cudaError_t launch_t1_kinematics(const float* q, float* p, float* J, int B, cudaStream_t stream);
+cudaError_t launch_t1_ik(const float* p, float* q, int B, cudaStream_t stream);
 // host entry: one chunk of inputs from mapped pinned host memory into device staging, co-resident with a running solve
 cudaError_t launch_prefetch(const double* const* src, double* const* dst, const int* n, const float* rot_src, float* rot_dst,
                             int rot_n, int ctas, cudaStream_t stream);

@@ -220,6 +220,17 @@ int srbd_gait(float* gait_phase, const float* dt_mpc, const int* ssp_durations, 
 int srbd_reference_trajectory(const float* const* f32in9, double step, float* world_position_desired, float* yaw_desired,
                               unsigned char* first_run, float* x0, float* x_ref, int B, void* stream);
 
+/* ---- batched kinematics of the T1 biped ------------------------------------------------------ *
+ * Replaces T1.forward_kinematics / get_p0e / contact_jacobian (core/robot/t1.py:96-138), which evaluate the four
+ * CasADi functions casadi/t1_kinematics.py:39-75 generates from model/t1_serial.urdf on the CPU for env 0 only.
+ * joint_angle: device fp32 (B,2,6) [left, right] x [Hip_Pitch, Hip_Roll, Hip_Yaw, Knee_Pitch, Ankle_Pitch, Ankle_Roll];
+ * foot_position: (B,2,3) sole position in the trunk frame; jacobian: (B,2,6,6) LOCAL_WORLD_ALIGNED frame Jacobian, rows
+ * [linear, angular], columns = joints.  Either output may be NULL.  fp64 arithmetic inside, fp32 results (the reference
+ * evaluates in double and casts, t1.py:113,137). */
+int srbd_t1_kinematics(const float* joint_angle, float* foot_position, float* jacobian, int B, void* stream);
+/* T1.analytical_IK (t1.py:139-213): foot_position (B,2,3) trunk frame -> joint_angle (B,2,6), hip yaw = ankle roll = 0. */
+int srbd_t1_inverse_kinematics(const float* foot_position, float* joint_angle, int B, void* stream);
+
 /* u0 = x[120:132] -> body-frame wrench (B,2,6) fp32, mpc_controller_cusadi.py:186-203.
  * rotation_body: device fp32 (B,3,3) row-major. */
 int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, int B, void* stream);

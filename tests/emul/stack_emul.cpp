@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "srbd_stack_impl.h"
+#include "srbd_t1_impl.h"
 
 using namespace srbd;
 
@@ -46,6 +47,16 @@ int srbd_emul_reference_trajectory(const float* const* f32in9, double step, floa
   a.v_des_b = f32in9[5]; a.w_des_b = f32in9[6]; a.height = f32in9[7]; a.dt_mpc = f32in9[8];
   a.step = (float)step; a.wpd = wpd; a.yaw_des = yaw_des; a.first_run = first_run; a.x0 = x0; a.x_ref = x_ref;
   for (long long e = 0; e < B; ++e) reference_trajectory_env(a, e);
+  return 0;
+}
+
+// batched T1 kinematics (csrc/srbd_t1_impl.h), one (env, leg) pair after the other
+int srbd_emul_t1_kinematics(const float* q, float* p, float* J, int B) {
+  for (long long i = 0; i < 2LL * B; ++i) t1_fk_jac(q + 6 * i, (int)(i & 1), p ? p + 3 * i : nullptr, J ? J + 36 * i : nullptr);
+  return 0;
+}
+int srbd_emul_t1_ik(const float* p, float* q, int B) {
+  for (long long i = 0; i < 2LL * B; ++i) t1_ik(p + 3 * i, (int)(i & 1), q + 6 * i);
   return 0;
 }
 

@@ -141,7 +141,7 @@ def stack_emul_lib():
     src = os.path.join(ROOT, "tests", "emul", "stack_emul.cpp")
     out = os.path.join(ROOT, "tests", "emul", "libstack_emul.so")
     csrc = os.path.join(ROOT, "biped-pympc_b200", "csrc")
-    deps = [src, os.path.join(csrc, "srbd_stack_impl.h"), os.path.join(ROOT, "include", "srbd_mpc.h")]
+    deps = [src, os.path.join(csrc, "srbd_stack_impl.h"), os.path.join(csrc, "srbd_t1_impl.h"), os.path.join(ROOT, "include", "srbd_mpc.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-I", csrc, src,
                         "-o", out], check=True)
