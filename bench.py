@@ -299,6 +299,39 @@ def sub_converge(bp, torch, dev, local_rank, flush, steps=3):
             "what": "BASELINE configs[3]: run to convergence, beyond the reference's 5-iteration codegen limit"}
 
 
+def sub_fp32_mode(bp, torch, dev, local_rank, flush, ref_ms, steps=10):
+    """north_star's optional fp32 mode (include/srbd_mpc.h SRBD_F32_FACTOR / _REFINE / _REFINE2), measured on the metric's
+    4 096-env workload: time of the fused tick per mode and the worst per-env relative error of x after the 5 iterations
+    against this repo's own fp64 path (which the parity tests hold within 1e-9 of the 80-bit oracle)."""
+    B = 4096
+    inp, rot = bp.workload.make_batch(B, seed=20261018)
+    ins = [torch.as_tensor(a, device=dev) for a in inp]
+    rot_t = torch.as_tensor(rot, dtype=torch.float32, device=dev)
+    ctx = bp.Context(B, local_rank)
+    x64 = ctx.solve(ins, rot_t, num_calls=1, iters_per_call=ITERS, want_iterates=True)[1]
+    out = {"what": "optional reduced-precision mode: fp32 Schur pivot blocks (formed, coupled, inverted, stored in fp32) with 0 / 1 / 2 "
+                   "steps of iterative refinement per solve against the fp64 operator; err_x = max over envs of |x - x_fp64| / |x_fp64| "
+                   "after 5 iterations; stated tolerance 1e-4 = the two-step mode",
+           "fp64_ms_per_step": ref_ms, "modes": {}}
+    for mode in ("f32", "f32_refined", "f32_refined2"):
+        ctx.set_precision(mode)
+        x = ctx.solve(ins, rot_t, num_calls=1, iters_per_call=ITERS, want_iterates=True)[1]
+        err = float(((x - x64).norm(dim=1) / x64.norm(dim=1)).max().item())
+        for _ in range(2):
+            ctx.solve(ins, rot_t, num_calls=1, iters_per_call=ITERS)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            flush.fill_(1.0)
+            a.record()
+            ctx.solve(ins, rot_t, num_calls=1, iters_per_call=ITERS)
+            b.record()
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+        out["modes"][mode] = {"ms_per_step": ms, "value": B / (ms * 1e-3), "unit": UNIT, "err_x": err, "speed_vs_fp64": ref_ms / ms}
+    ctx.close()
+    return out
+
+
 def sub_closed_loop():
     """BASELINE configs[4]: gait generator + swing leg + MPC at 4 096 envs for 1 000 control steps (tests/closed_loop_stack.py:
     BipedControllerB200 in closed loop with a single-rigid-body stand-in plant; only the controller calls are timed)."""
@@ -757,7 +790,8 @@ def run_b200(args):
                         "h2d_bytes_per_step": sum(a.numel() * 8 for a in hi) + hr.numel() * 4, "d2h_bytes_per_step": hw.numel() * 4}
             line["e2e_all17_pinned"] = e2e_case(True)
             line["e2e_all17_pageable"] = e2e_case(False)
-            for key, fn in (("converge_16384", lambda: sub_converge(bp, torch, dev, local_rank, flush)),
+            for key, fn in (("fp32_mode", lambda: sub_fp32_mode(bp, torch, dev, local_rank, flush, line["ms_per_step"])),
+                            ("converge_16384", lambda: sub_converge(bp, torch, dev, local_rank, flush)),
                             ("closed_loop_4096x1000", sub_closed_loop),
                             ("compat_dropin", lambda: run_compat(argparse.Namespace(envs=B), emit=False))):
                 try:

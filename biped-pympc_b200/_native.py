@@ -13,13 +13,16 @@ LIB_PATH = os.environ.get("SRBD_MPC_LIB") or os.path.join(HERE, "lib", "libsrbd_
 
 COLD_START = 1
 STAGE_INVARIANT = 2
+F32_FACTOR, F32_REFINE, F32_REFINE2 = 4, 8, 16      # optional reduced-precision mode (include/srbd_mpc.h)
+PRECISIONS = {"f64": 0, "f32": 1, "f32_refined": 2, "f32_refined2": 3}   # srbd_ctx_set_precision / pdipm(precision=)
+_PRECISION_FLAGS = {0: 0, 1: F32_FACTOR, 2: F32_FACTOR | F32_REFINE, 3: F32_FACTOR | F32_REFINE2}
 
 QP_NNZ_IN = (12, 120, 120, 120, 1, 1, 1, 9, 9, 3, 3, 3, 20, 12, 12, 3, 3)
 QP_NNZ_OUT = (240, 240, 1196, 140, 280, 160)
 IP_NNZ_IN = (240, 280, 1196, 240, 160, 140, 240, 160, 160, 140)
 IP_NNZ_OUT = (240, 160, 160, 140, 4, 1)
 WORK_DOUBLES = 6224          # general kernel, per env (srbd_args.h PDIPM_WORK_DOUBLES)
-WORK_DOUBLES_FAST = 1024     # fast kernel (STAGE_INVARIANT), per env
+WORK_DOUBLES_FAST = 1408     # fast kernel (STAGE_INVARIANT), per env (the fp64 path touches the first 1 024)
 
 _lib = None
 _P = ctypes.POINTER(ctypes.c_double)
@@ -29,7 +32,7 @@ EXPORTED_SYMBOLS = (
     "srbd_version", "srbd_error_string", "srbd_last_cuda_error", "srbd_init",
     "srbd_qp_former_nnz_in", "srbd_qp_former_nnz_out", "srbd_pdipm_nnz_in", "srbd_pdipm_nnz_out",
     "srbd_pattern", "srbd_loop_buffers_size", "srbd_update_state", "srbd_lowlevel", "srbd_gait", "srbd_reference_trajectory", "srbd_marshal_inputs", "srbd_marshal_inputs_iw", "srbd_qp_form", "srbd_pdipm_work_doubles", "srbd_pdipm", "srbd_pdipm_is_stage_invariant", "srbd_wrench",
-    "srbd_ctx_create", "srbd_ctx_destroy", "srbd_mpc_solve", "srbd_mpc_solve_warm", "srbd_mpc_solve_host",
+    "srbd_ctx_create", "srbd_ctx_destroy", "srbd_ctx_set_precision", "srbd_mpc_solve", "srbd_mpc_solve_warm", "srbd_mpc_solve_host",
     "srbd_qp_former_evaluate", "srbd_sparse_pdipm_multiple_iterations_evaluate", "srbd_dfma_peak",
     "srbd_t1_kinematics", "srbd_t1_inverse_kinematics",
 )
@@ -73,6 +76,7 @@ def load(build_if_missing: bool = True):
     lib.srbd_reference_trajectory.argtypes = [vp, cd, vp, vp, vp, vp, vp, ci, vp]
     lib.srbd_ctx_create.argtypes = [ctypes.POINTER(vp), ci, ci]
     lib.srbd_ctx_destroy.argtypes = [vp]
+    lib.srbd_ctx_set_precision.argtypes = [vp, ci]
     lib.srbd_mpc_solve.argtypes = [vp, vp, vp, ci, ci, ci, cd, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.srbd_mpc_solve_warm.argtypes = [vp, vp, vp, ci, ci, cd, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.srbd_mpc_solve_host.argtypes = [vp, vp, vp, ci, ci, ci, cd, vp, vp, vp]
@@ -277,9 +281,12 @@ def is_stage_invariant(inputs: Sequence) -> bool:
 
 
 def pdipm(inputs: Sequence, num_iters: int = 5, tol: float = 0.0, cold_start: bool = False,
-          stage_invariant: bool = False, out: Optional[List] = None, work=None, iters_done=None) -> List:
+          stage_invariant: bool = False, out: Optional[List] = None, work=None, iters_done=None,
+          precision: str = "f64") -> List:
     """sparse_pdipm_multiple_iterations with a runtime iteration count.
     inputs: [Q_val, G_val, A_val, f, h, b, x, s, z, y] (x,s,z,y may be None with cold_start).
+    precision: "f64" (parity path) | "f32" | "f32_refined" | "f32_refined2" (optional reduced-precision modes of the fast
+    kernel, include/srbd_mpc.h; need stage_invariant=True).
     Returns [x, s, z, y, residuals(B,4), mu(B,1)]."""
     import torch
     lib = load()
@@ -298,7 +305,7 @@ def pdipm(inputs: Sequence, num_iters: int = 5, tol: float = 0.0, cold_start: bo
         _check_buffers("pdipm out", out, IP_NNZ_OUT, B, dev)
         if any(o is None for o in out):
             raise ValueError("pdipm out: all six output tensors are required")
-    flags = (COLD_START if cold_start else 0) | (STAGE_INVARIANT if stage_invariant else 0)
+    flags = (COLD_START if cold_start else 0) | (STAGE_INVARIANT if stage_invariant else 0) | _PRECISION_FLAGS[PRECISIONS[precision]]
     per_env = WORK_DOUBLES_FAST if stage_invariant else WORK_DOUBLES     # = srbd_pdipm_work_doubles(1, flags)
     if work is None:
         work = torch.empty((B, per_env), dtype=torch.float64, device=dev)
@@ -343,6 +350,11 @@ class Context:
         self._h = ctypes.c_void_p()
         check(lib.srbd_ctx_create(ctypes.byref(self._h), int(max_B), int(device)))
         self.max_B = max_B
+
+    def set_precision(self, precision: str = "f64"):
+        """Precision of the ticks this context launches: "f64" (default, parity path), "f32", "f32_refined",
+        "f32_refined2" (include/srbd_mpc.h: optional reduced-precision mode)."""
+        check(load().srbd_ctx_set_precision(self._h, PRECISIONS[precision]))
 
     def close(self):
         if getattr(self, "_h", None):

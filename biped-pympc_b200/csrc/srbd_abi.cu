@@ -136,6 +136,7 @@ struct srbd_ctx {
   int have_prev = 0;                      // envs whose (x, y) of the previous srbd_mpc_solve_warm are in it[]
   int have_sched = 0;                     // envs whose previous contact schedule is in work[] (any fused tick writes it)
   bool unfused = false;                   // SRBD_TICK_UNFUSED=1: assembly, solve and wrench as three launches
+  int precision = 0;                      // PdipmArgs::precision of the ticks this context launches (srbd_ctx_set_precision)
 };
 
 extern "C" {
@@ -226,6 +227,8 @@ int srbd_pdipm(const double* const* in10, double* const* out6, double* work, int
   a.work = work; a.work_stride = fast ? PDIPM_WORK_DOUBLES_FAST : PDIPM_WORK_DOUBLES; a.inv_flag = nullptr;
   a.iters_done = iters_done; a.num_iters = num_iters; a.tol = tol; a.cold_start = cold ? 1 : 0;
   a.fused = 0; a.rot = nullptr; a.wrench = nullptr; a.warm_xy = 0; a.reset = nullptr;
+  a.precision = (flags & SRBD_F32_FACTOR) ? ((flags & SRBD_F32_REFINE2) ? 3 : ((flags & SRBD_F32_REFINE) ? 2 : 1)) : 0;
+  if (a.precision && !fast) return SRBD_EINVAL;   // the reduced-precision blocks exist in the fast kernel only
   for (int i = 0; i < QP_N_IN; ++i) a.qp_in[i] = nullptr;
   SRBD_CUDA(launch_pdipm(a, B, fast, num_sms(), (cudaStream_t)stream));
   return SRBD_OK;
@@ -357,6 +360,12 @@ int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, 
 }
 
 // ---- context -----------------------------------------------------------------------------
+int srbd_ctx_set_precision(srbd_ctx* c, int mode) {
+  if (!c || mode < SRBD_PRECISION_F64 || mode > SRBD_PRECISION_F32_REFINED2) return SRBD_EINVAL;
+  c->precision = mode;
+  return SRBD_OK;
+}
+
 int srbd_ctx_destroy(srbd_ctx* c) {
   if (!c) return SRBD_OK;
   cudaSetDevice(c->device);
@@ -432,7 +441,7 @@ int solve_range(srbd_ctx* c, const double* const* in17, const float* rotation_bo
     a.work = c->work + o * PDIPM_WORK_DOUBLES_FAST; a.work_stride = PDIPM_WORK_DOUBLES_FAST; a.inv_flag = nullptr;
     a.iters_done = iters_done; a.num_iters = iters; a.tol = tol;
     a.cold_start = 1; a.fused = 1; a.rot = rotation_body; a.wrench = wrench;
-    a.warm_xy = warm; a.reset = reset;
+    a.warm_xy = warm; a.reset = reset; a.precision = c->precision;
     SRBD_CUDA(launch_pdipm(a, B, true, num_sms(), st));
     return SRBD_OK;
   }
@@ -444,7 +453,8 @@ int solve_range(srbd_ctx* c, const double* const* in17, const float* rotation_bo
                                  nullptr, nullptr, nullptr, nullptr};
   double* out6[IP_N_OUT] = {x, s, z, y, res, c->mu + o};
   rc = srbd_pdipm(in10, out6, c->work + o * PDIPM_WORK_DOUBLES_FAST, iters_done, B, iters, tol,
-                  SRBD_COLD_START | SRBD_STAGE_INVARIANT, st);
+                  SRBD_COLD_START | SRBD_STAGE_INVARIANT | (c->precision ? SRBD_F32_FACTOR : 0u) |
+                      (c->precision == 2 ? SRBD_F32_REFINE : 0u) | (c->precision == 3 ? SRBD_F32_REFINE2 : 0u), st);
   if (rc) return rc;
   if (wrench) return srbd_wrench(x, rotation_body, wrench, B, st);
   return SRBD_OK;
@@ -650,7 +660,7 @@ float srbd_sparse_pdipm_multiple_iterations_evaluate(const double** inputs, doub
     for (int i = 0; i < IP_N_OUT; ++i) { if (!hout[i]) return (int)SRBD_EINVAL; a.out[i] = hout[i]; }
     a.work = ws->work; a.work_stride = PDIPM_WORK_DOUBLES_FAST; a.inv_flag = ws->flag;
     a.iters_done = nullptr; a.num_iters = 5; a.tol = 0.0; a.cold_start = 0;
-    a.fused = 0; a.rot = nullptr; a.wrench = nullptr; a.warm_xy = 0; a.reset = nullptr;
+    a.fused = 0; a.rot = nullptr; a.wrench = nullptr; a.warm_xy = 0; a.reset = nullptr; a.precision = 0;
     for (int i = 0; i < QP_N_IN; ++i) a.qp_in[i] = nullptr;
     // in10[6..9] may alias out6[0..3]; the fast kernel copies the iterates first, so a rerun needs the originals:
     // when they alias, the (rare) general-kernel fallback cannot be taken after the fact, so probe up front instead

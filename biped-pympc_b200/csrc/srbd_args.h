@@ -21,6 +21,9 @@ struct PdipmArgs {
   int* iters_done;              // optional (B) per-env Newton iterations executed
   int num_iters;                // Newton iterations per call (runtime, reference bakes 5)
   double tol;                   // <= 0: fixed iteration count; > 0: stop when rx,rs,re,mu < tol
+  int precision;                // 0: fp64 throughout (the parity path).  Fast kernel only -- 1: the ten Schur pivot blocks are
+                                //   formed, coupled, inverted and stored in fp32; 2 / 3: the same plus one / two steps of
+                                //   iterative refinement per solve against the fp64 operator
   int cold_start;               // 1: ignore in[x,s,z,y]; start from x=0, s=max(h,1), z=1, y=1
                                 //    (mpc_controller_cusadi.py:138-141)
   // ---- fused tick (fast kernel only): assemble from the 17 qp_former inputs instead of reading
@@ -38,6 +41,7 @@ struct PdipmArgs {
 };
 constexpr int PDIPM_WORK_DOUBLES = 6224;  // general kernel, per env: directions + per-row barrier data (1 344) and the ten
                                           // stage buffers prepared once per call (10 x 488)
-constexpr int PDIPM_WORK_DOUBLES_FAST = 1024;   // fast kernel (SRBD_STAGE_INVARIANT, fused tick): srbd_pdipm_fast.h FW_END
+constexpr int PDIPM_WORK_DOUBLES_FAST = 1408;   // fast kernel (SRBD_STAGE_INVARIANT, fused tick): srbd_pdipm_fast.h FW_END; the
+                                                // fp64 path touches the first 1 024
 
 }  // namespace srbd

@@ -98,6 +98,17 @@ struct alignas(16) dbl2 { double x, y; };
 SRBD_DEV double rcp(double x) { return 1.0 / x; }
 #endif
 
+// single-precision counterparts (the optional fp32 pivot-block mode of srbd_pdipm_fast.h)
+#if defined(__CUDACC__) && !defined(SRBD_HOST_EMUL)
+typedef float4 flt4;
+SRBD_DEV float rcp(float x) { return __frcp_rn(x); }
+#else
+struct alignas(16) flt4 { float x, y, z, w; };
+SRBD_DEV float rcp(float x) { return 1.0f / x; }
+#endif
+SRBD_DEV double fmaR(double a, double b, double c) { return fma(a, b, c); }
+SRBD_DEV float fmaR(float a, float b, float c) { return fmaf(a, b, c); }
+
 SRBD_DEV int pk(int i, int j) { return i >= j ? ((i * (i + 1)) >> 1) + j : ((j * (j + 1)) >> 1) + i; }
 // 12 doubles from a 16-byte aligned shared-memory address
 SRBD_DEV void ld12(const double* p, double v[12]) {
@@ -111,6 +122,17 @@ SRBD_DEV void st12(double* p, const double v[12]) {
   dbl2* q = reinterpret_cast<dbl2*>(p);
 #pragma unroll
   for (int i = 0; i < 6; ++i) { dbl2 t; t.x = v[2 * i]; t.y = v[2 * i + 1]; q[i] = t; }
+}
+
+SRBD_DEV void ld12(const float* p, float v[12]) {
+  const flt4* q = reinterpret_cast<const flt4*>(p);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { const flt4 t = q[i]; v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
+}
+SRBD_DEV void st12(float* p, const float v[12]) {
+  flt4* q = reinterpret_cast<flt4*>(p);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { flt4 t; t.x = v[4 * i]; t.y = v[4 * i + 1]; t.z = v[4 * i + 2]; t.w = v[4 * i + 3]; q[i] = t; }
 }
 
 template <bool kUniform>

@@ -22,6 +22,8 @@
 // emulator of srbd_warp.h.
 #pragma once
 
+#include <type_traits>
+
 #include "srbd_pdipm_core.h"
 #include "srbd_qp_table.h"
 
@@ -58,7 +60,9 @@ struct FastSmem {
 // lane-private per-row scratch in the work buffer
 enum : int { FW_DX = 0, FW_DY = 240, FW_S = 380, FW_Z = 540, FW_Q = 700,
              // fused tick only: f of the states, c_d | c_d + A_d x0, F_max * contact
-             FW_FX = 860, FW_CD = 980, FW_FC = 1004, FW_END = 1024 };
+             FW_FX = 860, FW_CD = 980, FW_FC = 1004,
+             // fp32 pivot blocks with refinement only: re of the iteration (r4 of the affine solve), the unrefined dx
+             FW_RE = 1024, FW_RX = 1152, FW_END = 1392 };
 static_assert(FW_END <= PDIPM_WORK_DOUBLES_FAST, "work buffer too small");
 
 // host: gather table of the fast path from the table of srbd_stage_table.h
@@ -84,8 +88,15 @@ SRBD_DEV float wrench_entry(const double* u0, const float* R, int idx) {
   return -(R[0 + i] * v0 + R[3 + i] * v1 + R[6 + i] * v2);
 }
 
-struct PdipmFast {
+// kF32 = false: everything in fp64 (the parity path).  kF32 = true, the optional reduced-precision mode
+// (SRBD_PRECISION_F32_FACTOR): the ten Schur pivot blocks are formed, coupled, inverted and stored in fp32 -- the part
+// of a Newton step with the matrix-matrix work -- while residuals, right-hand sides, the block-Thomas recurrences and
+// the iterates stay in fp64; with `refine` the two solves of an iteration are each followed by one step of iterative
+// refinement against the fp64 Schur operator.  Accuracy and speed are measured, not promised: DESIGN.md section 8.
+template <bool kF32>
+struct PdipmFastT {
   using SM = FastSmem;
+  using R = typename std::conditional<kF32, float, double>::type;   // precision of the pivot blocks
   Warp w;
   double* sm;
   const StageSlot* slots;
@@ -111,11 +122,12 @@ struct PdipmFast {
   SRBD_DEV double* gout(int i, int nnz) const { return pa->out[i] + e * nnz; }
   SRBD_DEV double* gws() const { return pa->work + e * (long long)pa->work_stride; }
 
-  SRBD_DEV double* P(int k) const { return sm + SM::OFF_P + 78 * k; }
+  SRBD_DEV R* P(int k) const { return reinterpret_cast<R*>(sm + SM::OFF_P) + 78 * k; }
   SRBD_DEV double* fb() const { return sm + SM::OFF_FB; }
   SRBD_DEV double* bc() const { return sm + SM::OFF_BC + 24 * h; }
   SRBD_DEV double* tr() const { return sm + SM::OFF_TR + 32 * h; }
-  SRBD_DEV double* pr(int hh) const { return sm + SM::OFF_PR + 72 * hh; }
+  SRBD_DEV R* pr(int hh) const { return reinterpret_cast<R*>(sm + SM::OFF_PR) + 72 * hh; }
+  SRBD_DEV R* bcr() const { return reinterpret_cast<R*>(sm + SM::OFF_BC + 24 * h); }   // broadcast scratch in block precision
   SRBD_DEV double* psi(int k) const { return sm + SM::OFF_PSI + 14 * k; }
 
   // ------------------------------------------------------------------------------------
@@ -372,43 +384,46 @@ struct PdipmFast {
   // ------------------------------------------------------------------------------------
   // row rr of S_kk into a[12]
   // ------------------------------------------------------------------------------------
-  SRBD_DEV void form_row(int k, double a[12]) const {
+  SRBD_DEV void form_row(int k, R a[12]) const {
     const double* f = fb();
     const double* ps = psi(k);
     const double* der = f + FB_DER;
-    double* b = bc();
-    double wv[12];
-    double sL, sR;
+    R* b = bcr();
+    R wv[12];
+    R sL, sR;
     {
-      double Brow[12];
-      ld12(f + FB_B + 14 * rr, Brow);
-      double psv[14];
+      double Bd[12];
+      ld12(f + FB_B + 14 * rr, Bd);
+      R Brow[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) Brow[i] = (R)Bd[i];
+      R psv[14];
       const dbl2* q = reinterpret_cast<const dbl2*>(ps);
 #pragma unroll
-      for (int i = 0; i < 7; ++i) { const dbl2 t = q[i]; psv[2 * i] = t.x; psv[2 * i + 1] = t.y; }
-      const double pL = psv[3] * Brow[0] + psv[4] * Brow[1] + psv[5] * Brow[7] - Brow[2];
-      const double pR = psv[10] * Brow[3] + psv[11] * Brow[4] + psv[12] * Brow[10] - Brow[5];
+      for (int i = 0; i < 7; ++i) { const dbl2 t = q[i]; psv[2 * i] = (R)t.x; psv[2 * i + 1] = (R)t.y; }
+      const R pL = psv[3] * Brow[0] + psv[4] * Brow[1] + psv[5] * Brow[7] - Brow[2];
+      const R pR = psv[10] * Brow[3] + psv[11] * Brow[4] + psv[12] * Brow[10] - Brow[5];
       b[rr] = pL; b[12 + rr] = pR;
-      wv[0] = psv[0] * Brow[0]; wv[1] = psv[1] * Brow[1]; wv[2] = 0.0;
-      wv[3] = psv[7] * Brow[3]; wv[4] = psv[8] * Brow[4]; wv[5] = 0.0;
-      wv[6] = der[2] * Brow[6]; wv[7] = psv[2] * Brow[7]; wv[8] = der[0] * Brow[8];
-      wv[9] = der[3] * Brow[9]; wv[10] = psv[9] * Brow[10]; wv[11] = der[1] * Brow[11];
+      wv[0] = psv[0] * Brow[0]; wv[1] = psv[1] * Brow[1]; wv[2] = (R)0;
+      wv[3] = psv[7] * Brow[3]; wv[4] = psv[8] * Brow[4]; wv[5] = (R)0;
+      wv[6] = (R)der[2] * Brow[6]; wv[7] = psv[2] * Brow[7]; wv[8] = (R)der[0] * Brow[8];
+      wv[9] = (R)der[3] * Brow[9]; wv[10] = psv[9] * Brow[10]; wv[11] = (R)der[1] * Brow[11];
       sL = psv[6] * pL; sR = psv[13] * pR;
     }
     // state part: delta + phix on the diagonal, A phix A' (absent for k = 0: x_0 is a parameter)
-    const double fk = (k == 0) ? 0.0 : 1.0;
-    const double dg = phx_rr + IP_DELTA;
+    const R fk = (k == 0) ? (R)0 : (R)1;
+    const R dg = (R)(phx_rr + IP_DELTA);
 #pragma unroll
-    for (int j = 0; j < 12; ++j) a[j] = fma(fk, f[FB_SX + prow[j]], (rr == j) ? dg : 0.0);
+    for (int j = 0; j < 12; ++j) a[j] = fmaR(fk, (R)f[FB_SX + prow[j]], (rr == j) ? dg : (R)0);
     w.sync();
     {
-      double pl[12];
+      R pl[12];
       ld12(b, pl);
 #pragma unroll
-      for (int j = 0; j < 12; ++j) a[j] = fma(sL, pl[j], a[j]);
+      for (int j = 0; j < 12; ++j) a[j] = fmaR(sL, pl[j], a[j]);
       ld12(b + 12, pl);
 #pragma unroll
-      for (int j = 0; j < 12; ++j) a[j] = fma(sR, pl[j], a[j]);
+      for (int j = 0; j < 12; ++j) a[j] = fmaR(sR, pl[j], a[j]);
     }
 #pragma unroll
     for (int j = 0; j < 12; ++j) {
@@ -416,48 +431,48 @@ struct PdipmFast {
       if (j < 3 || (j >= 6 && j < 9)) {          // dense rows of Bbar (euler, omega)
         double bj[12];
         ld12(Bj, bj);
-        double q0 = 0.0, q1 = 0.0;
+        R q0 = (R)0, q1 = (R)0;
 #pragma unroll
         for (int c = 0; c < 12; c += 2) {
-          if (c != 2) q0 = fma(wv[c], bj[c], q0);
-          if (c + 1 != 5) q1 = fma(wv[c + 1], bj[c + 1], q1);
+          if (c != 2) q0 = fmaR(wv[c], (R)bj[c], q0);
+          if (c + 1 != 5) q1 = fmaR(wv[c + 1], (R)bj[c + 1], q1);
         }
         a[j] += q0 + q1;
       } else {                                    // position / velocity rows: two entries
         const int c1_ = (j < 6) ? j - 3 : j - 9, c2_ = c1_ + 3;
-        a[j] = fma(wv[c1_], Bj[c1_], fma(wv[c2_], Bj[c2_], a[j]));
+        a[j] = fmaR(wv[c1_], (R)Bj[c1_], fmaR(wv[c2_], (R)Bj[c2_], a[j]));
       }
     }
   }
 
   // n -= M P M' with M the coupling of `type`; own = row rr of P, hand = handed-over rows
-  SRBD_DEV void couple(double n[12], const double own[12], const double* hand, int type) const {
-    const double cv0 = type ? c1[0] : c0[0], cv1 = type ? c1[1] : c0[1];
-    const double cv2 = type ? c1[2] : c0[2], cv3 = type ? c1[3] : c0[3];
+  SRBD_DEV void couple(R n[12], const R own[12], const R* hand, int type) const {
+    const R cv0 = (R)(type ? c1[0] : c0[0]), cv1 = (R)(type ? c1[1] : c0[1]);
+    const R cv2 = (R)(type ? c1[2] : c0[2]), cv3 = (R)(type ? c1[3] : c0[3]);
     const int base = type ? 0 : 6;
     int s1 = (type ? i1[0] : i0[0]) - base, s2 = (type ? i1[1] : i0[1]) - base, s3 = (type ? i1[2] : i0[2]) - base;
     s1 = s1 < 0 ? 0 : (s1 > 5 ? 5 : s1); s2 = s2 < 0 ? 0 : (s2 > 5 ? 5 : s2); s3 = s3 < 0 ? 0 : (s3 > 5 ? 5 : s3);
-    double U[12];
+    R U[12];
     {
-      double t1[12];
+      R t1[12];
       ld12(hand + 12 * s1, t1);
 #pragma unroll
-      for (int m = 0; m < 12; ++m) U[m] = fma(cv1, t1[m], cv0 * own[m]);
+      for (int m = 0; m < 12; ++m) U[m] = fmaR(cv1, t1[m], cv0 * own[m]);
       ld12(hand + 12 * s2, t1);
 #pragma unroll
-      for (int m = 0; m < 12; ++m) U[m] = fma(cv2, t1[m], U[m]);
+      for (int m = 0; m < 12; ++m) U[m] = fmaR(cv2, t1[m], U[m]);
       ld12(hand + 12 * s3, t1);
 #pragma unroll
-      for (int m = 0; m < 12; ++m) U[m] = fma(cv3, t1[m], U[m]);
+      for (int m = 0; m < 12; ++m) U[m] = fmaR(cv3, t1[m], U[m]);
     }
     const double* cm = fb() + FB_CM + 36 * type;
 #pragma unroll
     for (int cc = 0; cc < 12; ++cc) {
-      double o = U[cc] * cm[cc];
-      if (cc < 3) o += U[6] * cm[12 + 3 * cc] + U[7] * cm[12 + 3 * cc + 1] + U[8] * cm[12 + 3 * cc + 2];
-      else if (cc < 6) o += U[cc + 6] * cm[21 + cc - 3];
-      else if (cc < 9) o += U[0] * cm[24 + 3 * (cc - 6)] + U[1] * cm[24 + 3 * (cc - 6) + 1] + U[2] * cm[24 + 3 * (cc - 6) + 2];
-      else o += U[cc - 6] * cm[33 + cc - 9];
+      R o = U[cc] * (R)cm[cc];
+      if (cc < 3) o += U[6] * (R)cm[12 + 3 * cc] + U[7] * (R)cm[12 + 3 * cc + 1] + U[8] * (R)cm[12 + 3 * cc + 2];
+      else if (cc < 6) o += U[cc + 6] * (R)cm[21 + cc - 3];
+      else if (cc < 9) o += U[0] * (R)cm[24 + 3 * (cc - 6)] + U[1] * (R)cm[24 + 3 * (cc - 6) + 1] + U[2] * (R)cm[24 + 3 * (cc - 6) + 2];
+      else o += U[cc - 6] * (R)cm[33 + cc - 9];
       n[cc] -= o;
     }
   }
@@ -467,25 +482,25 @@ struct PdipmFast {
   // pivot row p (one 8-byte store per lane instead of a 96-byte row).  The pivot row is scaled
   // immediately: keeping it unscaled with a deferred factor costs 100x in the residual
   // |P S - I| (measured), although the entrywise error is the same.
-  SRBD_DEV void sweep_invert(double a[12]) const {
-    double* b = bc();
+  SRBD_DEV void sweep_invert(R a[12]) const {
+    R* b = bcr();
     w.sync();   // the broadcast scratch still holds form_row's exchange
 #pragma unroll
     for (int p = 0; p < 12; ++p) {
-      double* bp = b + 12 * (p & 1);
+      R* bp = b + 12 * (p & 1);
       bp[rr] = a[p];
       w.sync();
-      double bv[12];
+      R bv[12];
       ld12(bp, bv);
-      const double di = rcp(bv[p]);
+      const R di = rcp(bv[p]);
       const bool piv = (rr == p);
-      const double t = a[p] * di;
+      const R t = a[p] * di;
       if (piv) {
 #pragma unroll
         for (int c = 0; c < 12; ++c) if (c != p) a[c] = bv[c] * di;
       } else {
 #pragma unroll
-        for (int c = 0; c < 12; ++c) if (c != p) a[c] = fma(-t, bv[c], a[c]);
+        for (int c = 0; c < 12; ++c) if (c != p) a[c] = fmaR(-t, bv[c], a[c]);
       }
       a[p] = piv ? -di : t;
     }
@@ -498,30 +513,30 @@ struct PdipmFast {
     // round 4: top k = 4 ; bottom idle
     // round 5: top k = 5 with both couplings (from 4 and from 6)
     // The own row of the neighbour's inverse is re-read from the packed storage, the three other
-    // rows a lane needs come from the 72-double hand-over window.
+    // rows a lane needs come from the 72-entry hand-over window.
 #pragma unroll 1
     for (int t = 0; t < 6; ++t) {
       const int k = (t == 5) ? 5 : (h ? 9 - t : t);
       const bool act = (t < 4) || (h == 0);
-      double n[12];
+      R n[12];
       form_row(k, n);
       if (t > 0) {
-        double o[12];
-        const double* Pn = P((t == 5) ? 4 : (h ? k + 1 : k - 1));
+        R o[12];
+        const R* Pn = P((t == 5) ? 4 : (h ? k + 1 : k - 1));
 #pragma unroll
         for (int c = 0; c < 12; ++c) o[c] = Pn[prow[c]];
         couple(n, o, pr(h), h);
       }
       if (t == 5) {
-        double o[12];
-        const double* P6 = P(6);
+        R o[12];
+        const R* P6 = P(6);
 #pragma unroll
         for (int c = 0; c < 12; ++c) o[c] = P6[prow[c]];
         couple(n, o, pr(1), 1);
       }
       sweep_invert(n);
       if (act) {
-        double* Pk = P(k);
+        R* Pk = P(k);
 #pragma unroll
         for (int c = 0; c < 12; ++c) if (c <= rr) Pk[prow[c]] = n[c];
         const int slot = h ? rr : rr - 6;
@@ -534,11 +549,13 @@ struct PdipmFast {
   // ------------------------------------------------------------------------------------
   // block-Thomas solve on vy[0..119]  (rho -> t -> dy), twisted
   // ------------------------------------------------------------------------------------
-  SRBD_DEV double prow_dot(const double* Pm, const double v[12]) const {
+  // row rr of a packed pivot-block inverse times the 12-vector v (fp32 blocks: the stored entries are widened, the
+  // products and sums are fp64 -- with fp32 products the refined mode stops at 2e-4 instead of 1e-5)
+  SRBD_DEV double prow_dot(const R* Pm, const double v[12]) const {
     double q0 = 0.0, q1 = 0.0, q2 = 0.0;
 #pragma unroll
     for (int m = 0; m < 12; m += 3) {
-      q0 = fma(Pm[prow[m]], v[m], q0); q1 = fma(Pm[prow[m + 1]], v[m + 1], q1); q2 = fma(Pm[prow[m + 2]], v[m + 2], q2);
+      q0 = fma((double)Pm[prow[m]], v[m], q0); q1 = fma((double)Pm[prow[m + 1]], v[m + 1], q1); q2 = fma((double)Pm[prow[m + 2]], v[m + 2], q2);
     }
     return q0 + q1 + q2;
   }
@@ -743,6 +760,7 @@ struct PdipmFast {
 #pragma unroll 1
           for (int t = 0; t < 5; ++t) recover(h ? 9 - t : t, pass, bc8, mn_s, mn_z);
         }
+        if (kF32) for (int q = 2; q <= A.precision; ++q) refine(pass, mn_s, mn_z);
         if (pass == 0) {
           w.sync();
           double* ws = gws();
@@ -928,6 +946,7 @@ struct PdipmFast {
         }
         a_re = fma(valid * re, re, a_re);
         vy[12 * k + rr] = re;
+        if (kF32 && pa->precision >= 2) ws[FW_RE + 12 * k + rr] = re;
         if (r >= 12 && r < 14) {   // Mx rows
           const double rm = u[6 + 3 * (r - 12)] - bm;
           a_re = fma(rm, rm, a_re);
@@ -958,6 +977,58 @@ struct PdipmFast {
     double gdg, gz;
     gather_col(trd, nullptr, gdg, gz);
     vx[120 + 12 * k + rr] = -gdg;
+    w.sync();
+  }
+
+  // fp32 pivot blocks only: one step of iterative refinement of the solve just recovered.  With dx = Phi^-1 (r1~ - A' dy)
+  // the residual of the Schur system is e = rho - S dy = A dx - delta dy - r4, evaluated here in fp64 from the recovered
+  // step (the Mx rows and their inputs were eliminated in closed form and carry no error); S ddy = e is solved with the
+  // same fp32 blocks and the correction is recovered like a corrector solve with a zero right-hand side (r1~ = 0,
+  // r4 = 0), whose ds / dz parts accumulate onto the lane-private slots.  Measured: DESIGN.md section 8.
+  SRBD_DEV void refine(int pass, double& mn_s, double& mn_z) {
+    const double* f = fb();
+    double* vx = sm + SM::OFF_VX;
+    double* vy = sm + SM::OFF_VY;
+    double* keep = sm + SM::OFF_PR;   // the hand-over window is only live inside factor(): 144 >= 140 doubles
+    double* ws = gws();
+    w.sync();
+    for (int i = lane; i < NEQ; i += 32) keep[i] = vy[i];
+    for (int i = lane; i < NZ; i += 32) ws[FW_RX + i] = vx[i];
+    double ev[5];
+    {
+      double Brow[12];
+      ld12(f + FB_B + 14 * rr, Brow);
+      const double h0 = f[FB_HX + rr] + IP_BETA, h1 = f[FB_HX + i0[0]] + IP_BETA, h2 = f[FB_HX + i0[1]] + IP_BETA, h3 = f[FB_HX + i0[2]] + IP_BETA;
+#pragma unroll 1
+      for (int t = 0; t < 5; ++t) {
+        const int k = h ? 9 - t : t;
+        double uv[12];
+        ld12(vx + 120 + 12 * k, uv);
+        double e = vx[12 * k + rr] + dot12(Brow, uv) - IP_DELTA * vy[12 * k + rr];
+        if (k >= 1) {
+          const double* xp = vx + 12 * (k - 1);
+          e += c0[0] * h0 * xp[rr] + c0[1] * h1 * xp[i0[0]] + c0[2] * h2 * xp[i0[1]] + c0[3] * h3 * xp[i0[2]];
+        }
+        if (pass == 0) e += ws[FW_RE + 12 * k + rr];   // - r4 = + re
+        ev[t] = e;
+      }
+    }
+    w.sync();
+#pragma unroll
+    for (int t = 0; t < 5; ++t) if (r < 12) vy[12 * (h ? 9 - t : t) + rr] = ev[t];
+    for (int i = lane; i < 120; i += 32) vx[120 + i] = 0.0;
+    w.sync();
+    solve_thomas();
+    mn_s = 1e300; mn_z = 1e300;
+    {
+      double bc8[8];
+      ld_bcol(bc8);
+#pragma unroll 1
+      for (int t = 0; t < 5; ++t) recover(h ? 9 - t : t, 1, bc8, mn_s, mn_z);
+    }
+    w.sync();
+    for (int i = lane; i < NZ; i += 32) vx[i] += ws[FW_RX + i];
+    for (int i = lane; i < NEQ; i += 32) vy[i] += keep[i];
     w.sync();
   }
 
@@ -1002,5 +1073,6 @@ struct PdipmFast {
     }
   }
 };
+using PdipmFast = PdipmFastT<false>;
 
 }  // namespace srbd

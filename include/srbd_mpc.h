@@ -64,6 +64,18 @@ extern "C" {
                                      fast kernel.  Non-unit coefficients are detected per env and
                                      reported as NaN iterates / iters_done = -1               */
 
+/* OPTIONAL reduced-precision mode of the fast kernel (north_star: "an optional fp32 mode with a stated tolerance of <= 1e-4";
+ * the reference has no such mode).  Requires SRBD_STAGE_INVARIANT; SRBD_EINVAL otherwise.
+ *   SRBD_F32_FACTOR     the ten 12x12 Schur pivot blocks of a Newton step are formed, coupled, inverted and stored in fp32;
+ *                       residuals, right-hand sides, the block recurrences and the iterates stay fp64.  Alone it is NOT within
+ *                       1e-4: iterates within 6e-2 of the fp64 path after the reference's 5 iterations.
+ *   | SRBD_F32_REFINE   plus one step of iterative refinement per solve against the fp64 operator: 3e-4 after 5 iterations
+ *   | SRBD_F32_REFINE2  plus two steps: STATED TOLERANCE 1e-4 on x, s, z, y after 5 iterations (measured 1.3e-6; 2e-4 ... 6e-4
+ *                       after 10).  Slower than the fp64 path: each refinement step costs a block-Thomas solve. */
+#define SRBD_F32_FACTOR 4u
+#define SRBD_F32_REFINE 8u
+#define SRBD_F32_REFINE2 16u
+
 #define SRBD_NZ 240
 #define SRBD_NEQ 140
 #define SRBD_NINEQ 160
@@ -97,7 +109,7 @@ int srbd_pattern(char which /* 'H','A','G' */, const int** colptr, const int** r
 int srbd_qp_form(const double* const* in17, double* const* out6, int B, void* stream);
 
 /* scratch doubles the caller must provide to srbd_pdipm for B environments when it is called with
- * `flags`: 1 024 per env with SRBD_STAGE_INVARIANT (the fast kernel), 6 224 per env without (the general
+ * `flags`: 1 408 per env with SRBD_STAGE_INVARIANT (the fast kernel), 6 224 per env without (the general
  * kernel parks its ten prepared stage buffers there). */
 size_t srbd_pdipm_work_doubles(int B, unsigned flags);
 
@@ -239,6 +251,15 @@ int srbd_wrench(const double* x_sol, const float* rotation_body, float* wrench, 
 typedef struct srbd_ctx srbd_ctx;
 int srbd_ctx_create(srbd_ctx** ctx, int max_B, int device);
 int srbd_ctx_destroy(srbd_ctx* ctx);
+/* precision of the fused ticks this context launches (srbd_mpc_solve, srbd_mpc_solve_warm, srbd_mpc_solve_host):
+ * SRBD_PRECISION_F64 (default, the parity path), SRBD_PRECISION_F32 = SRBD_F32_FACTOR above,
+ * SRBD_PRECISION_F32_REFINED = SRBD_F32_FACTOR | SRBD_F32_REFINE, SRBD_PRECISION_F32_REFINED2 = SRBD_F32_FACTOR |
+ * SRBD_F32_REFINE2 (the mode with the stated 1e-4 tolerance). */
+#define SRBD_PRECISION_F64 0
+#define SRBD_PRECISION_F32 1
+#define SRBD_PRECISION_F32_REFINED 2
+#define SRBD_PRECISION_F32_REFINED2 3
+int srbd_ctx_set_precision(srbd_ctx* ctx, int mode);
 /* form -> cold start -> num_calls x iters_per_call Newton iterations -> wrench, device
  * buffers in / out (mpc_controller_cusadi.py:97-203 without the host round trips).
  *   x_out/s_out/z_out/y_out/res_out: optional device buffers (NULL = not wanted)        */

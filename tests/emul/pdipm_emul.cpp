@@ -37,16 +37,23 @@ static void run_env(const PdipmArgs& A, long long e, const StageSlot* slots, int
   });
 }
 
-static void run_env_fast(const PdipmArgs& A, long long e, const StageSlot* slots) {
+static int g_f32_factor = 0;   // PdipmArgs::precision: 1 / 2 = the reduced-precision pivot-block mode (PdipmFastT<true>)
+template <bool kF32>
+static void run_env_fast_t(const PdipmArgs& A, long long e, const StageSlot* slots) {
   std::vector<double> smem(FastSmem::SIZE, 0.0);
   run_warp([&](int lane) {
-    PdipmFast W;
+    PdipmFastT<kF32> W;
     W.w.lane_ = lane;
     W.sm = smem.data();
     W.slots = slots;
     W.run(A, e);
   });
 }
+static void run_env_fast(const PdipmArgs& A, long long e, const StageSlot* slots) {
+  if (g_f32_factor) run_env_fast_t<true>(A, e, slots);
+  else run_env_fast_t<false>(A, e, slots);
+}
+extern "C" void srbd_emul_set_f32_factor(int on) { g_f32_factor = on; }
 
 extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, double* work, int* iters_done,
                                int B, int num_iters, double tol, int cold_start, int uniform, int trace) {
@@ -58,7 +65,7 @@ extern "C" int srbd_emul_pdipm(const double* const* in10, double* const* out6, d
   for (int i = 0; i < IP_N_IN; ++i) A.in[i] = in10[i];
   for (int i = 0; i < IP_N_OUT; ++i) A.out[i] = out6[i];
   A.work = work; A.work_stride = PDIPM_WORK_DOUBLES; A.inv_flag = nullptr; A.iters_done = iters_done; A.num_iters = num_iters; A.tol = tol; A.cold_start = cold_start;
-  A.fused = 0; A.rot = nullptr; A.wrench = nullptr; A.warm_xy = 0; A.reset = nullptr;
+  A.precision = g_f32_factor; A.fused = 0; A.rot = nullptr; A.wrench = nullptr; A.warm_xy = 0; A.reset = nullptr;
   for (int i = 0; i < QP_N_IN; ++i) A.qp_in[i] = nullptr;
   g_trace_on = trace != 0;
   g_trace.clear();
@@ -83,7 +90,7 @@ extern "C" int srbd_emul_tick(const double* const* in17, const float* rot, doubl
   for (int i = 0; i < QP_N_IN; ++i) A.qp_in[i] = in17[i];
   for (int i = 0; i < IP_N_OUT; ++i) A.out[i] = out6[i];
   A.work = work; A.work_stride = PDIPM_WORK_DOUBLES; A.inv_flag = nullptr; A.iters_done = iters_done; A.num_iters = num_iters; A.tol = tol; A.cold_start = 1;
-  A.fused = 1; A.rot = rot; A.wrench = wrench; A.warm_xy = warm; A.reset = reset;
+  A.precision = g_f32_factor; A.fused = 1; A.rot = rot; A.wrench = wrench; A.warm_xy = warm; A.reset = reset;
   g_trace_on = false;
   (void)pair;
   for (long long e = 0; e < B; ++e) run_env_fast(A, e, fslots);

@@ -68,8 +68,9 @@ def emul_lib():
     return _EMUL
 
 
-def emul_pdipm(qp, iters, x=None, s=None, z=None, y=None, tol=0.0, uniform=True, lane_order=1):
+def emul_pdipm(qp, iters, x=None, s=None, z=None, y=None, tol=0.0, uniform=True, lane_order=1, precision=0):
     """Runs the PDIPM *device code* under the CPU warp emulator.  Returns (outs6, iters_done).
+    precision: PdipmArgs::precision of the fast kernel (0 fp64; 1 / 2 / 3 = fp32 pivot blocks + 0 / 1 / 2 refinement steps).
     uniform: False = general kernel (srbd_pdipm_core.h, arbitrary values on the pattern),
              True / 2 = stage-invariant fast kernel (srbd_pdipm_fast.h),
              1 = stage-invariant instantiation of the general kernel."""
@@ -90,8 +91,10 @@ def emul_pdipm(qp, iters, x=None, s=None, z=None, y=None, tol=0.0, uniform=True,
     inarr = (P * 10)(*[a.ctypes.data_as(P) for a in ins])
     outarr = (P * 6)(*[a.ctypes.data_as(P) for a in outs])
     lib.srbd_emul_set_order(int(lane_order))
+    lib.srbd_emul_set_f32_factor(int(precision))
     lib.srbd_emul_pdipm(inarr, outarr, work.ctypes.data_as(P), itd.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
                         B, int(iters), ctypes.c_double(tol), int(cold), int(uniform), 0)
+    lib.srbd_emul_set_f32_factor(0)
     return outs, itd
 
 

@@ -51,6 +51,22 @@ def test_emulated_kernel_against_golden(golden):
         assert rel_err(got20[i], golden[f"ip20_{n}"]) < 1e-6
 
 
+def test_optional_fp32_mode_tolerances(qp_small):
+    """The optional reduced-precision mode (include/srbd_mpc.h SRBD_F32_FACTOR / _REFINE / _REFINE2): fp32 pivot blocks
+    alone are NOT within north_star's 1e-4 (measured 6e-2 on x: du of the unconstrained yaw moments is dy / 1e-4); every
+    refinement step against the fp64 operator gains a factor of about 200; two steps are the mode with the STATED
+    TOLERANCE 1e-4 after the reference's 5 iterations (measured 1.3e-6).  Same device code as the GPU kernel."""
+    ref = oracle_ip_batch(qp_small, 5, dtype=np.longdouble)
+    worst = {}
+    for prec in (1, 2, 3):
+        got, itd = emul_pdipm(qp_small, 5, precision=prec)
+        assert list(itd) == [5] * 4
+        worst[prec] = max(rel_err(got[i][e], ref[i][e]) for i in range(4) for e in range(4))
+    assert worst[3] < 1e-4, worst                     # the stated tolerance
+    assert worst[3] < worst[2] < worst[1] < 0.5       # refinement helps monotonically; unrefined is usable only as a preconditioner
+    assert worst[2] < 5e-3 and worst[1] > 1e-4
+
+
 def test_continuation_equals_single_call(qp_small):
     """4 x 5 chained calls (mpc_controller_cusadi.py:144-169) == one 20-iteration call."""
     a, _ = emul_pdipm(qp_small, 10)
