@@ -508,18 +508,26 @@ struct PdipmFastT {
     for (int c = 0; c < 12; ++c) a[c] = -a[c];
   }
 
-  SRBD_DEV void factor() {
+  // fwd: the forward substitution of the affine solve (t_next -= M (P_k t_k), solve_thomas) is done here, at the end of
+  // each round, while the lane's row of P_k is still in registers (saves the packed re-read of five mat-vecs)
+  SRBD_DEV void factor(bool fwd) {
     // rounds 0..3: top k = t (coupling from k-1) | bottom k = 9-t (coupling from k+1)
-    // round 4: top k = 4 ; bottom idle
-    // round 5: top k = 5 with both couplings (from 4 and from 6)
+    // round 4: top k = 4 | bottom: S_55 - C_6' P_6 C_6 (block 5 with its coupling from 6), parked packed in P(5)
+    // round 5: top k = 5: the parked rows, coupling from 4, sweep ; bottom idle
     // The own row of the neighbour's inverse is re-read from the packed storage, the three other
     // rows a lane needs come from the 72-entry hand-over window.
+    double* vy = sm + SM::OFF_VY;
 #pragma unroll 1
     for (int t = 0; t < 6; ++t) {
       const int k = (t == 5) ? 5 : (h ? 9 - t : t);
       const bool act = (t < 4) || (h == 0);
       R n[12];
-      form_row(k, n);
+      if (t < 5) form_row(k, n);
+      else {
+        const R* P5 = P(5);
+#pragma unroll
+        for (int c = 0; c < 12; ++c) n[c] = P5[prow[c]];
+      }
       if (t > 0) {
         R o[12];
         const R* Pn = P((t == 5) ? 4 : (h ? k + 1 : k - 1));
@@ -527,14 +535,32 @@ struct PdipmFastT {
         for (int c = 0; c < 12; ++c) o[c] = Pn[prow[c]];
         couple(n, o, pr(h), h);
       }
-      if (t == 5) {
-        R o[12];
-        const R* P6 = P(6);
+      if (t == 4 && h == 1) {
+        R* P5 = P(5);
 #pragma unroll
-        for (int c = 0; c < 12; ++c) o[c] = P6[prow[c]];
-        couple(n, o, pr(1), 1);
+        for (int c = 0; c < 12; ++c) if (c <= rr) P5[prow[c]] = n[c];
       }
       sweep_invert(n);
+      if (fwd && t < 5) {
+        double tv[12];
+        ld12(vy + 12 * k, tv);
+        double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+#pragma unroll
+        for (int m = 0; m < 12; m += 3) {
+          q0 = fma((double)n[m], tv[m], q0); q1 = fma((double)n[m + 1], tv[m + 1], q1); q2 = fma((double)n[m + 2], tv[m + 2], q2);
+        }
+        double* b = bc();
+        // fp64: the sweep's last pivot row sits in the second half of the scratch, slots 0..11 are free; the fp32 sweep's
+        // two 12-float buffers overlap them
+        if (kF32) w.sync();
+        b[rr] = q0 + q1 + q2;
+        w.sync();
+        const double cv0 = h ? c1[0] : c0[0], cv1 = h ? c1[1] : c0[1], cv2 = h ? c1[2] : c0[2], cv3 = h ? c1[3] : c0[3];
+        const int j1 = h ? i1[0] : i0[0], j2 = h ? i1[1] : i0[1], j3 = h ? i1[2] : i0[2];
+        const double d = cv0 * b[rr] + cv1 * b[j1] + cv2 * b[j2] + cv3 * b[j3];
+        const int kn = (t < 3) ? (h ? k - 1 : k + 1) : (t == 3 ? (h ? 5 : 4) : 5);
+        if (act && r < 12) vy[12 * kn + rr] -= d;
+      }
       if (act) {
         R* Pk = P(k);
 #pragma unroll
@@ -559,13 +585,13 @@ struct PdipmFastT {
     }
     return q0 + q1 + q2;
   }
-  SRBD_DEV void solve_thomas() {
+  SRBD_DEV void solve_thomas(bool fwd_done = false) {
     double* vy = sm + SM::OFF_VY;
     double* b = bc();
     // forward: t_k -= M (P_nb t_nb).  t = 4: the bottom half applies C_6' (from 6) to block 5,
-    // t = 5: the top half applies C_5 (from 4)
+    // t = 5: the top half applies C_5 (from 4).  fwd_done: factor(true) has already done it
 #pragma unroll 1
-    for (int t = 1; t < 6; ++t) {
+    for (int t = fwd_done ? 6 : 1; t < 6; ++t) {
       int k, nb;
       if (t < 4) { k = h ? 9 - t : t; nb = h ? k + 1 : k - 1; }
       else if (t == 4) { k = h ? 5 : 4; nb = h ? 6 : 3; }
@@ -748,10 +774,10 @@ struct PdipmFastT {
         }
         if (pass == 0) {
           SRBD_TRACE("rho_aff", vy, 140);
-          factor();
+          factor(true);
           SRBD_TRACE("P", sm + SM::OFF_P, 780);
         }
-        solve_thomas();
+        solve_thomas(pass == 0);
         if (pass == 0) SRBD_TRACE("dyd_aff", vy, 120);
         mn_s = 1e300; mn_z = 1e300;   // min over ALL 160 candidates (1.0 where dv >= 0): may exceed 1
         {

@@ -1,0 +1,283 @@
+// Developer prototype (round 2): inversion of the 12x12 SPD Schur pivot blocks of the PDIPM kernel with FP64 tensor-core
+// instructions (mma.sync.m8n8k4.f64, "DMMA") against the row-per-lane symmetric sweep the product kernel uses
+// (srbd_pdipm_fast.h::sweep_invert).  Same occupancy as the product kernel: 148 CTAs x 14 warps, two blocks per warp per
+// round (the two fronts of the twisted block elimination), blocks read from and written to packed-lower shared memory.
+//
+//   sweep   half-warp per block, lane = row; per pivot: one 8-byte store per lane, a warp barrier, the pivot row
+//           broadcast from shared memory (6 x LDS.128 = 12 wavefronts), 12 FMAs per lane
+//   dmma    warp per block, the block lives in four 8x8 accumulator tiles (two doubles per lane and tile); blocked
+//           Gauss-Jordan with 4x4 pivot blocks = the k of the instruction.  An accumulator tile doubles as two A (or, by
+//           symmetry, B) fragments -- its even and its odd columns -- so a pivot set is {0,2,4,6}, {1,3,5,7} or
+//           {8,10,12,14} in position space (positions 9,11,13,15 are padding); per block step: the 4x4 pivot block goes
+//           through shared memory to every lane (2 + 10 wavefronts), every lane solves D x = e_t for its column by LDL',
+//           G = -L D^-1 by two DMMAs, the rank-4 update by four, the pivot rows of the other two column sets are
+//           patched with two 64-bit shuffles (4 wavefronts)
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/dmma_gj_proto tools/dmma_gj_proto.cu
+//   tools/dmma_gj_proto [reps]          prints ms, blocks/s and the worst |P S - I| of both variants
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
+
+constexpr int kWarps = 14;
+constexpr int kSmemPerWarp = 2066;   // doubles: the product kernel's footprint, so that occupancy matches
+
+__host__ __device__ inline int pk(int i, int j) { return i >= j ? ((i * (i + 1)) >> 1) + j : ((j * (j + 1)) >> 1) + i; }
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b, double c0, double c1) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+               : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// variant 1: the product kernel's sweep (half-warp per block)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld12(const double* p, double v[12]) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { const double2 t = q[i]; v[2 * i] = t.x; v[2 * i + 1] = t.y; }
+}
+
+__global__ void __launch_bounds__(32 * kWarps, 1) sweep_kernel(const double* S, double* P, int reps) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4, r = lane & 15, rr = r < 12 ? r : 11;
+  double* sm = smem + warp * kSmemPerWarp;
+  double* Sin = sm + 78 * h;            // packed input block of this half
+  double* Pout = sm + 156 + 78 * h;     // packed result
+  double* b = sm + 312 + 24 * h;        // broadcast scratch, double buffered
+  const long long blk = ((long long)blockIdx.x * kWarps + warp) * 2 + h;
+  for (int i = r; i < 78; i += 16) Sin[i] = S[blk * 78 + i];
+  __syncwarp();
+  int prow[12];
+#pragma unroll
+  for (int m = 0; m < 12; ++m) prow[m] = pk(rr, m);
+#pragma unroll 1
+  for (int rep = 0; rep < reps; ++rep) {
+    double a[12];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) a[c] = Sin[prow[c]];
+#pragma unroll
+    for (int p = 0; p < 12; ++p) {
+      double* bp = b + 12 * (p & 1);
+      bp[rr] = a[p];
+      __syncwarp();
+      double bv[12];
+      ld12(bp, bv);
+      const double di = 1.0 / bv[p];
+      const bool piv = (rr == p);
+      const double t = a[p] * di;
+      if (piv) {
+#pragma unroll
+        for (int c = 0; c < 12; ++c) if (c != p) a[c] = bv[c] * di;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 12; ++c) if (c != p) a[c] = fma(-t, bv[c], a[c]);
+      }
+      a[p] = piv ? -di : t;
+    }
+#pragma unroll
+    for (int c = 0; c < 12; ++c) if (c <= rr) Pout[prow[c]] = -a[c];
+    __syncwarp();
+  }
+  for (int i = r; i < 78; i += 16) P[blk * 78 + i] = Pout[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// variant 2: blocked Gauss-Jordan on accumulator tiles
+// ---------------------------------------------------------------------------------------------------------------------
+// position (0..15) -> matrix index (0..11) or -1 for padding
+__device__ __forceinline__ int pos2idx(int p) { return p < 8 ? p : ((p & 1) ? -1 : 8 + ((p - 8) >> 1)); }
+
+struct Tile16 {
+  double a[2][2][2];   // [row tile I][col tile J][slot s]: lane (g, t) holds M[8I + g][8J + 2t + s]
+};
+
+// x = D^-1 e_col, element `row`, D symmetric positive definite 4x4 given by its lower triangle d[pk(i,j)]
+__device__ __forceinline__ double inv4_elem(const double d[10], int col, int row) {
+  const double r0 = 1.0 / d[0];
+  const double l10 = d[1] * r0, l20 = d[3] * r0, l30 = d[6] * r0;
+  const double d1 = fma(-l10, d[1], d[2]);
+  const double r1 = 1.0 / d1;
+  const double m21 = fma(-l20, d[1], d[4]), m31 = fma(-l30, d[1], d[7]);
+  const double l21 = m21 * r1, l31 = m31 * r1;
+  const double d2 = fma(-l21, m21, fma(-l20, d[3], d[5]));
+  const double r2 = 1.0 / d2;
+  const double m32 = fma(-l31, m21, fma(-l30, d[3], d[8]));
+  const double l32 = m32 * r2;
+  const double d3 = fma(-l32, m32, fma(-l31, m31, fma(-l30, d[6], d[9])));
+  const double r3 = 1.0 / d3;
+  // forward: L y = e_col
+  const double e0 = col == 0 ? 1.0 : 0.0, e1 = col == 1 ? 1.0 : 0.0, e2 = col == 2 ? 1.0 : 0.0, e3 = col == 3 ? 1.0 : 0.0;
+  const double y0 = e0;
+  const double y1 = fma(-l10, y0, e1);
+  const double y2 = fma(-l21, y1, fma(-l20, y0, e2));
+  const double y3 = fma(-l32, y2, fma(-l31, y1, fma(-l30, y0, e3)));
+  // diagonal, backward: L' x = z
+  const double x3 = y3 * r3;
+  const double x2 = fma(-l32, x3, y2 * r2);
+  const double x1 = fma(-l31, x3, fma(-l21, x2, y1 * r1));
+  const double x0 = fma(-l30, x3, fma(-l20, x2, fma(-l10, x1, y0 * r0)));
+  return row == 0 ? x0 : (row == 1 ? x1 : (row == 2 ? x2 : x3));
+}
+
+// one block step on pivot set (Jp, sp); dsm = 16 doubles of scratch
+template <int Jp, int sp>
+__device__ __forceinline__ void gj_step(Tile16& M, double* dsm, int g, int t) {
+  // ---- the 4x4 pivot block to every lane
+  const bool mine = ((g & 1) == sp);
+  if (mine) dsm[4 * (g >> 1) + t] = M.a[Jp][Jp][sp];
+  __syncwarp();
+  double d[10];
+  {
+    const double2* q = reinterpret_cast<const double2*>(dsm);
+    const double2 v0 = q[0], v2 = q[2], v3 = q[3], v4 = q[4], v5 = q[5], v7 = q[7];
+    d[0] = v0.x; d[1] = v2.x; d[2] = v2.y; d[3] = v4.x; d[4] = v4.y; d[5] = v5.x;
+    const double2 v6 = q[6];
+    d[6] = v6.x; d[7] = v6.y; d[8] = v7.x; d[9] = v7.y;
+    (void)v3;
+  }
+  __syncwarp();
+  // ---- this lane's element of D^-1: column t, row g >> 1 (the same element serves the B fragment of G = -L D^-1 and
+  //      the overwrite of the pivot block)
+  const double x = inv4_elem(d, t, g >> 1);
+  const double bfrag = (g & 1) ? 0.0 : -x;       // B[k = t][n = g] = -Dinv[t][g / 2] for even n, 0 for odd n
+  // ---- G' = -L Dinv, in A layout (slot 0 of the result tile)
+  double G0, G1, z0, z1;
+  dmma(G0, z0, M.a[0][Jp][sp], bfrag, 0.0, 0.0);
+  dmma(G1, z1, M.a[1][Jp][sp], bfrag, 0.0, 0.0);
+  // ---- rank-4 update of every tile: M += G' L'   (B fragment of L' = the A fragment of L, by symmetry)
+  const double L0 = M.a[0][Jp][sp], L1 = M.a[1][Jp][sp];
+  dmma(M.a[0][0][0], M.a[0][0][1], G0, L0, M.a[0][0][0], M.a[0][0][1]);
+  dmma(M.a[0][1][0], M.a[0][1][1], G0, L1, M.a[0][1][0], M.a[0][1][1]);
+  dmma(M.a[1][0][0], M.a[1][0][1], G1, L0, M.a[1][0][0], M.a[1][0][1]);
+  dmma(M.a[1][1][0], M.a[1][1][1], G1, L1, M.a[1][1][0], M.a[1][1][1]);
+  // ---- own column panel: M[:, K] = L Dinv = -G' ; pivot block: -Dinv
+  M.a[0][Jp][sp] = -G0;
+  M.a[1][Jp][sp] = -G1;
+  if (mine) M.a[Jp][Jp][sp] = -x;
+  // ---- pivot rows in the other column sets: M[K_a][K'_b] = M[K'_b][K_a] = (-G')[row K'_b][a], from lane (g' = 2b + s', t' = a)
+  //      of row tile J'
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int J2 = q >> 1, s2 = q & 1;          // (0,0), (0,1), (1,0)
+    if (J2 == Jp && s2 == sp) continue;
+    const int src = ((2 * t + s2) << 2) | (g >> 1);
+    const double give = (J2 == 0) ? -G0 : -G1;
+    const double got = __shfl_sync(0xffffffffu, give, src);
+    if (mine) M.a[Jp][J2][s2] = got;
+  }
+}
+
+__global__ void __launch_bounds__(32 * kWarps, 1) dmma_kernel(const double* S, double* P, int reps) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  double* sm = smem + warp * kSmemPerWarp;
+  const long long blk0 = ((long long)blockIdx.x * kWarps + warp) * 2;
+  for (int i = lane; i < 156; i += 32) sm[i] = S[blk0 * 78 + i];
+  __syncwarp();
+  // packed offsets of this lane's 8 entries (-1: padding)
+  int off[2][2][2];
+#pragma unroll
+  for (int I = 0; I < 2; ++I)
+#pragma unroll
+    for (int J = 0; J < 2; ++J)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int ri = pos2idx(8 * I + g), ci = pos2idx(8 * J + 2 * t + s);
+        off[I][J][s] = (ri < 0 || ci < 0) ? -1 : pk(ri, ci);
+      }
+#pragma unroll 1
+  for (int rep = 0; rep < reps; ++rep) {
+#pragma unroll 1
+    for (int hb = 0; hb < 2; ++hb) {
+      const double* Sin = sm + 78 * hb;
+      double* Pout = sm + 156 + 78 * hb;
+      double* dsm = sm + 312 + 16 * hb;
+      Tile16 M;
+#pragma unroll
+      for (int I = 0; I < 2; ++I)
+#pragma unroll
+        for (int J = 0; J < 2; ++J)
+#pragma unroll
+          for (int s = 0; s < 2; ++s) M.a[I][J][s] = off[I][J][s] >= 0 ? Sin[off[I][J][s]] : 0.0;
+      gj_step<0, 0>(M, dsm, g, t);
+      gj_step<0, 1>(M, dsm, g, t);
+      gj_step<1, 0>(M, dsm, g, t);
+      // result = -S^-1; lower triangle to packed storage
+#pragma unroll
+      for (int I = 0; I < 2; ++I)
+#pragma unroll
+        for (int J = 0; J < 2; ++J)
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int ri = pos2idx(8 * I + g), ci = pos2idx(8 * J + 2 * t + s);
+            if (ri >= 0 && ci >= 0 && ci <= ri) Pout[off[I][J][s]] = -M.a[I][J][s];
+          }
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < 156; i += 32) P[blk0 * 78 + i] = sm[156 + i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+static double check(const std::vector<double>& S, const std::vector<double>& P, int nblk) {
+  double worst = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    for (int i = 0; i < 12; ++i)
+      for (int j = 0; j < 12; ++j) {
+        long double acc = 0;
+        for (int k = 0; k < 12; ++k) acc += (long double)P[b * 78 + pk(i, k)] * S[b * 78 + pk(k, j)];
+        const double e = fabs((double)(acc - (i == j ? 1.0L : 0.0L)));
+        if (!(e <= worst)) worst = e;
+      }
+  }
+  return worst;
+}
+
+int main(int argc, char** argv) {
+  const int reps = argc > 1 ? atoi(argv[1]) : 200;
+  const int ctas = 148, nblk = ctas * kWarps * 2;
+  std::vector<double> S(nblk * 78), P1(nblk * 78), P2(nblk * 78);
+  srand(7);
+  for (int b = 0; b < nblk; ++b) {   // R R' + scaled diagonal: condition numbers 1e3 ... 1e5 like the Schur blocks
+    double R[12][12];
+    for (auto& row : R) for (double& v : row) v = rand() / (double)RAND_MAX - 0.5;
+    for (int i = 0; i < 12; ++i)
+      for (int j = 0; j <= i; ++j) {
+        double a = 0;
+        for (int k = 0; k < 12; ++k) a += R[i][k] * R[j][k] * (k < 4 ? 100.0 : 1.0);
+        S[b * 78 + pk(i, j)] = a + (i == j ? 1e-2 : 0.0);
+      }
+  }
+  double *dS, *dP;
+  CHECK(cudaMalloc(&dS, S.size() * 8)); CHECK(cudaMalloc(&dP, S.size() * 8));
+  CHECK(cudaMemcpy(dS, S.data(), S.size() * 8, cudaMemcpyHostToDevice));
+  const size_t smem = sizeof(double) * kSmemPerWarp * kWarps;
+  CHECK(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CHECK(cudaFuncSetAttribute(dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  printf("variant,ms,ns_per_block_pair_per_sm,max_abs_PS_minus_I   (%d CTAs x %d warps, %d rounds of two blocks per warp)\n", ctas, kWarps, reps);
+  for (int v = 0; v < 2; ++v) {
+    float best = 1e30f;
+    for (int trial = 0; trial < 4; ++trial) {
+      CHECK(cudaMemset(dP, 0, S.size() * 8));
+      cudaEventRecord(e0);
+      if (v == 0) sweep_kernel<<<ctas, 32 * kWarps, smem>>>(dS, dP, reps);
+      else dmma_kernel<<<ctas, 32 * kWarps, smem>>>(dS, dP, reps);
+      cudaEventRecord(e1);
+      CHECK(cudaEventSynchronize(e1));
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      if (trial > 0 && ms < best) best = ms;
+    }
+    std::vector<double>& P = v == 0 ? P1 : P2;
+    CHECK(cudaMemcpy(P.data(), dP, P.size() * 8, cudaMemcpyDeviceToHost));
+    printf("%s,%.4f,%.1f,%.3e\n", v == 0 ? "sweep" : "dmma", best, best * 1e6 / reps / kWarps, check(S, P, nblk));
+  }
+  return 0;
+}
