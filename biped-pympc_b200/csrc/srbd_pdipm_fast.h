@@ -65,6 +65,19 @@ enum : int { FW_DX = 0, FW_DY = 240, FW_S = 380, FW_Z = 540, FW_Q = 700,
              FW_RE = 1024, FW_RX = 1152, FW_END = 1392 };
 static_assert(FW_END <= PDIPM_WORK_DOUBLES_FAST, "work buffer too small");
 
+// Packed storage of the symmetric 12x12 blocks (P_k, A phix A'): row i keeps its entries (i, 0..i) contiguous, as in the
+// triangular layout pk() of srbd_pdipm_core.h, but the rows are laid out in the order 7 0 1 3 6 11 9 4 8 2 5 10.  When
+// the twelve lanes of a half-warp read column c of a block -- (c, 0..c) from row c, (i, c) from the rows i > c -- the
+// twelve 8-byte words then fall into twelve different bank pairs for every c: 2 wavefronts per 64-bit load instead of
+// the 3.5 of the triangular order (sum over c of the worst bank multiplicity: 12 against 21; found by annealing over row
+// orders, tools/pack_layout.py).  The address arithmetic keeps the triangular layout's form -- own row: base(rr) + m,
+// other rows: constant + rr -- so it costs no registers.
+SRBD_DEV int pkf_row(int i) {
+  constexpr int kRow[12] = {8, 9, 58, 11, 44, 61, 15, 0, 49, 34, 67, 22};
+  return kRow[i];
+}
+SRBD_DEV int pkf(int i, int j) { return i >= j ? pkf_row(i) + j : pkf_row(j) + i; }
+
 // host: gather table of the fast path from the table of srbd_stage_table.h
 inline void build_fast_slots(const StageSlot* sb, StageSlot* fs) {
   for (int i = 0; i < FB_NSLOT; ++i) { fs[i].kind = ST_ZERO; fs[i].rel = 0; }
@@ -183,7 +196,7 @@ struct PdipmFastT {
     w.sync();
     // ---- per-lane registers ----------------------------------------------------------
 #pragma unroll
-    for (int m = 0; m < 12; ++m) prow[m] = pk(rr, m);
+    for (int m = 0; m < 12; ++m) prow[m] = pkf(rr, m);
     bs0 = 3 + rr % 3; bs1 = 9 + rr % 3;
     phx_rr = f[FB_PHX + rr];
     {
@@ -222,7 +235,7 @@ struct PdipmFastT {
         double acc = c0[0] * PdipmWarp<true>::abar(A, j, q);
 #pragma unroll
         for (int a = 0; a < 3; ++a) acc += c0[1 + a] * PdipmWarp<true>::abar(A, j, i0[a]);
-        f[FB_SX + pk(q, j)] = acc;
+        f[FB_SX + pkf(q, j)] = acc;
       }
     }
     {   // inequality row r

@@ -173,6 +173,97 @@ __device__ __forceinline__ void gj_step(Tile16& M, double* dsm, int g, int t) {
   }
 }
 
+// the same step on the two blocks of a round at once: two independent dependency chains per warp
+template <int Jp, int sp>
+__device__ __forceinline__ void gj_step2(Tile16& MA, Tile16& MB, double* dsm, int g, int t) {
+  const bool mine = ((g & 1) == sp);
+  if (mine) { dsm[4 * (g >> 1) + t] = MA.a[Jp][Jp][sp]; dsm[16 + 4 * (g >> 1) + t] = MB.a[Jp][Jp][sp]; }
+  __syncwarp();
+  double dA[10], dB[10];
+  {
+    const double2* q = reinterpret_cast<const double2*>(dsm);
+    const double2 v0 = q[0], v2 = q[2], v4 = q[4], v5 = q[5], v6 = q[6], v7 = q[7];
+    dA[0] = v0.x; dA[1] = v2.x; dA[2] = v2.y; dA[3] = v4.x; dA[4] = v4.y; dA[5] = v5.x; dA[6] = v6.x; dA[7] = v6.y; dA[8] = v7.x; dA[9] = v7.y;
+    const double2 w0 = q[8], w2 = q[10], w4 = q[12], w5 = q[13], w6 = q[14], w7 = q[15];
+    dB[0] = w0.x; dB[1] = w2.x; dB[2] = w2.y; dB[3] = w4.x; dB[4] = w4.y; dB[5] = w5.x; dB[6] = w6.x; dB[7] = w6.y; dB[8] = w7.x; dB[9] = w7.y;
+  }
+  __syncwarp();
+  const double xA = inv4_elem(dA, t, g >> 1), xB = inv4_elem(dB, t, g >> 1);
+  const double bA = (g & 1) ? 0.0 : -xA, bB = (g & 1) ? 0.0 : -xB;
+  double GA0, GA1, GB0, GB1, z0, z1;
+  dmma(GA0, z0, MA.a[0][Jp][sp], bA, 0.0, 0.0);
+  dmma(GB0, z1, MB.a[0][Jp][sp], bB, 0.0, 0.0);
+  dmma(GA1, z0, MA.a[1][Jp][sp], bA, 0.0, 0.0);
+  dmma(GB1, z1, MB.a[1][Jp][sp], bB, 0.0, 0.0);
+  const double LA0 = MA.a[0][Jp][sp], LA1 = MA.a[1][Jp][sp], LB0 = MB.a[0][Jp][sp], LB1 = MB.a[1][Jp][sp];
+  dmma(MA.a[0][0][0], MA.a[0][0][1], GA0, LA0, MA.a[0][0][0], MA.a[0][0][1]);
+  dmma(MB.a[0][0][0], MB.a[0][0][1], GB0, LB0, MB.a[0][0][0], MB.a[0][0][1]);
+  dmma(MA.a[0][1][0], MA.a[0][1][1], GA0, LA1, MA.a[0][1][0], MA.a[0][1][1]);
+  dmma(MB.a[0][1][0], MB.a[0][1][1], GB0, LB1, MB.a[0][1][0], MB.a[0][1][1]);
+  dmma(MA.a[1][0][0], MA.a[1][0][1], GA1, LA0, MA.a[1][0][0], MA.a[1][0][1]);
+  dmma(MB.a[1][0][0], MB.a[1][0][1], GB1, LB0, MB.a[1][0][0], MB.a[1][0][1]);
+  dmma(MA.a[1][1][0], MA.a[1][1][1], GA1, LA1, MA.a[1][1][0], MA.a[1][1][1]);
+  dmma(MB.a[1][1][0], MB.a[1][1][1], GB1, LB1, MB.a[1][1][0], MB.a[1][1][1]);
+  MA.a[0][Jp][sp] = -GA0; MA.a[1][Jp][sp] = -GA1; MB.a[0][Jp][sp] = -GB0; MB.a[1][Jp][sp] = -GB1;
+  if (mine) { MA.a[Jp][Jp][sp] = -xA; MB.a[Jp][Jp][sp] = -xB; }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int J2 = q >> 1, s2 = q & 1;
+    if (J2 == Jp && s2 == sp) continue;
+    const int src = ((2 * t + s2) << 2) | (g >> 1);
+    const double gotA = __shfl_sync(0xffffffffu, (J2 == 0) ? -GA0 : -GA1, src);
+    const double gotB = __shfl_sync(0xffffffffu, (J2 == 0) ? -GB0 : -GB1, src);
+    if (mine) { MA.a[Jp][J2][s2] = gotA; MB.a[Jp][J2][s2] = gotB; }
+  }
+}
+
+__global__ void __launch_bounds__(32 * kWarps, 1) dmma2_kernel(const double* S, double* P, int reps) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  double* sm = smem + warp * kSmemPerWarp;
+  const long long blk0 = ((long long)blockIdx.x * kWarps + warp) * 2;
+  for (int i = lane; i < 156; i += 32) sm[i] = S[blk0 * 78 + i];
+  __syncwarp();
+  int off[2][2][2];
+#pragma unroll
+  for (int I = 0; I < 2; ++I)
+#pragma unroll
+    for (int J = 0; J < 2; ++J)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int ri = pos2idx(8 * I + g), ci = pos2idx(8 * J + 2 * t + s);
+        off[I][J][s] = (ri < 0 || ci < 0) ? -1 : pk(ri, ci);
+      }
+  double* dsm = sm + 312;
+#pragma unroll 1
+  for (int rep = 0; rep < reps; ++rep) {
+    Tile16 MA, MB;
+#pragma unroll
+    for (int I = 0; I < 2; ++I)
+#pragma unroll
+      for (int J = 0; J < 2; ++J)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          MA.a[I][J][s] = off[I][J][s] >= 0 ? sm[off[I][J][s]] : 0.0;
+          MB.a[I][J][s] = off[I][J][s] >= 0 ? sm[78 + off[I][J][s]] : 0.0;
+        }
+    gj_step2<0, 0>(MA, MB, dsm, g, t);
+    gj_step2<0, 1>(MA, MB, dsm, g, t);
+    gj_step2<1, 0>(MA, MB, dsm, g, t);
+#pragma unroll
+    for (int I = 0; I < 2; ++I)
+#pragma unroll
+      for (int J = 0; J < 2; ++J)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int ri = pos2idx(8 * I + g), ci = pos2idx(8 * J + 2 * t + s);
+          if (ri >= 0 && ci >= 0 && ci <= ri) { sm[156 + off[I][J][s]] = -MA.a[I][J][s]; sm[234 + off[I][J][s]] = -MB.a[I][J][s]; }
+        }
+    __syncwarp();
+  }
+  for (int i = lane; i < 156; i += 32) P[blk0 * 78 + i] = sm[156 + i];
+}
+
 __global__ void __launch_bounds__(32 * kWarps, 1) dmma_kernel(const double* S, double* P, int reps) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -260,16 +351,18 @@ int main(int argc, char** argv) {
   const size_t smem = sizeof(double) * kSmemPerWarp * kWarps;
   CHECK(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CHECK(cudaFuncSetAttribute(dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CHECK(cudaFuncSetAttribute(dmma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   printf("variant,ms,ns_per_block_pair_per_sm,max_abs_PS_minus_I   (%d CTAs x %d warps, %d rounds of two blocks per warp)\n", ctas, kWarps, reps);
-  for (int v = 0; v < 2; ++v) {
+  for (int v = 0; v < 3; ++v) {
     float best = 1e30f;
     for (int trial = 0; trial < 4; ++trial) {
       CHECK(cudaMemset(dP, 0, S.size() * 8));
       cudaEventRecord(e0);
       if (v == 0) sweep_kernel<<<ctas, 32 * kWarps, smem>>>(dS, dP, reps);
-      else dmma_kernel<<<ctas, 32 * kWarps, smem>>>(dS, dP, reps);
+      else if (v == 1) dmma_kernel<<<ctas, 32 * kWarps, smem>>>(dS, dP, reps);
+      else dmma2_kernel<<<ctas, 32 * kWarps, smem>>>(dS, dP, reps);
       cudaEventRecord(e1);
       CHECK(cudaEventSynchronize(e1));
       float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -277,7 +370,7 @@ int main(int argc, char** argv) {
     }
     std::vector<double>& P = v == 0 ? P1 : P2;
     CHECK(cudaMemcpy(P.data(), dP, P.size() * 8, cudaMemcpyDeviceToHost));
-    printf("%s,%.4f,%.1f,%.3e\n", v == 0 ? "sweep" : "dmma", best, best * 1e6 / reps / kWarps, check(S, P, nblk));
+    printf("%s,%.4f,%.1f,%.3e\n", v == 0 ? "sweep" : (v == 1 ? "dmma" : "dmma_two_blocks_interleaved"), best, best * 1e6 / reps / kWarps, check(S, P, nblk));
   }
   return 0;
 }
