@@ -128,7 +128,7 @@ struct PdipmFastT {
   int goa, gob, ca, cz;         // inequality row r: G(r, ca) = fb[goa], G(r, cz) = fb[gob]
   int psk, psi_i, psf;          // role of input column rr in Psi: kind, index, foot
   int doff, moff;               // fb offsets of its constant Psi diagonal / 1/mx_den (or of a zero)
-  int g_row0, g_cnt, g_ofs;     // rows / G values of input column rr
+  int g_src;                    // lane that ends up with sum_j G[j, rr] v_j in gather_rows (-1: the column has no rows)
   enum : int { FB_ZERO = FB_B + 12 };   // a structurally zero slot (pad column of Bbar)
 
   SRBD_DEV const double* gin(int i, int nnz) const { return pa->in[i] + e * nnz; }
@@ -256,13 +256,9 @@ struct PdipmFastT {
       } else if (c == 7 || c == 10) { psk = 0; psi_i = 2; }
       else if (c == 8 || c == 11) { psk = 2; psi_i = (c == 11); doff = FB_DER + psi_i; }
       else { psk = 3; psi_i = (c == 9); doff = FB_DER + 2 + psi_i; moff = FB_DER + 4 + psi_i; }
-      g_row0 = 0; g_cnt = 0; g_ofs = 0;
-      if (c < 6) {
-        const int ft = c / 3, qq = c % 3;
-        if (qq == 0) { g_row0 = 8 * ft; g_cnt = 2; g_ofs = 12 * ft; }
-        else if (qq == 1) { g_row0 = 8 * ft + 2; g_cnt = 2; g_ofs = 12 * ft + 2; }
-        else { g_row0 = 8 * ft; g_cnt = 8; g_ofs = 12 * ft + 4; }
-      } else if (c == 7 || c == 10) { const int ft = (c == 10); g_row0 = 8 * ft + 4; g_cnt = 2; g_ofs = 24 + 2 * ft; }
+      g_src = -1;
+      if (c < 6) g_src = (lane & 16) + 8 * (c / 3) + (c % 3 == 2 ? 6 : 2 * (c % 3));
+      else if (c == 7 || c == 10) g_src = (lane & 16) + 8 * (c == 10) + 4;
     }
     w.sync();
     return bad;
@@ -320,19 +316,18 @@ struct PdipmFastT {
     const double q = psk == 0 ? p[3 + psi_i] : (psk == 1 ? -1.0 : 0.0);
     return dg * v[rr] + q * (p[6] * dot);
   }
-  // over the rows of input column rr: sum_j G[j,c] a_j and sum_j G[j,c] b_j
-  SRBD_DEV void gather_col(const double* va, const double* vb, double& sa, double& sb_) const {
-    const double* g = fb() + FB_G + g_ofs;
-    double xa = 0.0, xb = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const bool on = i < g_cnt;
-      const double gv = on ? g[i] : 0.0;
-      const double a = on ? va[g_row0 + i] : 0.0;
-      xa = fma(gv, a, xa);
-      if (vb) { const double b = on ? vb[g_row0 + i] : 0.0; xb = fma(gv, b, xb); }
-    }
-    sa = xa; sb_ = xb;
+  // sum_j G[j, rr] v_j over the sixteen inequality rows of a stage, lane r holding v_r and its row's two coefficients
+  // (ga on column ca, gb on the foot's fz).  The rows of a foot are eight neighbouring lanes: the pairs (0,1) (2,3) (4,5)
+  // carry the fx, fy, my columns, all eight the fz column, so two butterflies and one delivery shuffle replace a
+  // shared-memory staging of v and eight strided re-reads per lane
+  SRBD_DEV double gather_rows(double v, double ga, double gb) const {
+    double pa = ga * v, pz = gb * v;
+    pa += w.shfl_xor(pa, 1);
+    pz += w.shfl_xor(pz, 1);
+    pz += w.shfl_xor(pz, 2);
+    pz += w.shfl_xor(pz, 4);
+    const double got = w.shfl(((r & 7) == 6) ? pz : pa, g_src < 0 ? lane : g_src);
+    return g_src < 0 ? 0.0 : got;
   }
   SRBD_DEV double dot12(const double a[12], const double b[12]) const {
     double q0 = 0.0, q1 = 0.0;
@@ -922,7 +917,7 @@ struct PdipmFastT {
       }
       const double* u = sx + 120 + 12 * k;
       double* ps = psi(k);
-      double* trd = tr();
+      double gdg, gz;
       {   // inequality row j
         const double ga = f[goa], gb = f[gob];
         const double pga = w.shfl_xor(ga, 1), pgb = w.shfl_xor(gb, 1);
@@ -934,7 +929,7 @@ struct PdipmFastT {
         const double Dg = fma(D, rs, -(q * zv));         // D (r2 / W - r3), r2 = -z, r3 = -rs
         ws[FW_S + j] = fma(IP_DELTA, Dg, -rs); ws[FW_Z + j] = Dg; ws[FW_Q + j] = q;
         Dsm[j] = D;
-        trd[r] = Dg; trd[16 + r] = zv;
+        gdg = gather_rows(Dg, ga, gb); gz = gather_rows(zv, ga, gb);
         a_sz = fma(sv, zv, a_sz); a_rs = fma(rs, rs, a_rs);
         // Psi: pairs (0,1)->fx (2,3)->fy (4,5)->my ; (6,7) -> fz only
         const double pD = w.shfl_xor(D, 1);
@@ -956,13 +951,10 @@ struct PdipmFastT {
         if (jj < 6 && !(jj & 1)) { ps[7 * ft + (jj >> 1)] = ia; ps[7 * ft + 3 + (jj >> 1)] = tq; }
         if (jj == 6) ps[7 * ft + 6] = rcp(f[FB_HU + cz] + IP_BETA + contrib);
       }
-      w.sync();
       {   // input column rr : rx_u and r1~_u
         const double* yk = sy + 12 * k;
         double acc = fma(f[FB_HU + rr], u[rr], fu) + bcol_dot(yk);
         if (psk == 3) acc += sy[120 + 2 * k + psi_i];
-        double gdg, gz;
-        gather_col(trd, trd + 16, gdg, gz);
         acc += gz;
         a_rx = fma(valid * acc, acc, a_rx);
         vx[120 + 12 * k + rr] = -acc - gdg;
@@ -1010,12 +1002,7 @@ struct PdipmFastT {
     const double r2 = -(rcp(sv) * (sv * zv + dsa * dza - smu));
     const double Dg = q * r2;
     ws[FW_S + j] = fma(IP_DELTA, Dg, dsa); ws[FW_Z + j] = dza + Dg;
-    double* trd = tr();
-    trd[r] = Dg;
-    w.sync();
-    double gdg, gz;
-    gather_col(trd, nullptr, gdg, gz);
-    vx[120 + 12 * k + rr] = -gdg;
+    vx[120 + 12 * k + rr] = -gather_rows(Dg, fb()[goa], fb()[gob]);
     w.sync();
   }
 
