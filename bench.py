@@ -589,13 +589,16 @@ def run_b200(args):
     h_in = [None if i in (1, 2) else torch.as_tensor(a).pin_memory() for i, a in enumerate(inp)]
     h_rot = torch.as_tensor(rot, dtype=torch.float32).pin_memory()
     h_w = torch.empty((B, 2, 6), dtype=torch.float32).pin_memory()
+    # the buffers are bound once (validation + pointer marshalling of 19 tensors, ~45 us of Python per call otherwise); every
+    # call below still moves every input byte host -> device and the wrench device -> host inside the timed region
+    host_tick = ctx.bind_host(h_in, h_rot, h_w)
     for _ in range(3):
-        ctx.solve_host(h_in, h_rot, h_w, num_calls=args.calls, iters_per_call=args.iters, tol=args.tol)
+        host_tick(args.calls, args.iters, args.tol)
     n_e2e = max(10, min(args.steps, 100))
     barrier()
     t0 = time.perf_counter()
     for _ in range(n_e2e):
-        ctx.solve_host(h_in, h_rot, h_w, num_calls=args.calls, iters_per_call=args.iters, tol=args.tol)   # synchronous
+        host_tick(args.calls, args.iters, args.tol)   # synchronous
     e2e_s = time.perf_counter() - t0
     if dist is not None:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -637,7 +640,7 @@ def run_b200(args):
                    "envs_per_gpu": B, "iters": args.calls * args.iters, "horizon": 10, "parallelism": f"env-sharded x{world}, no collective",
                    "l2": "256 MB buffer written between timed iterations (L2 flush)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": n_e2e, "api": "srbd_mpc_solve_host (pinned host buffers read and written over PCIe by the kernels themselves: the first 2058-env chunk in place, the second pulled into device staging by a co-resident prefetch kernel while the first solves)"},
+                "steps": n_e2e, "api": "Context.bind_host(...)() = srbd_mpc_solve_host on buffers validated once (pinned host buffers read and written over PCIe by the kernels themselves: the first 2058-env chunk in place, the second pulled into device staging by a co-resident prefetch kernel while the first solves)"},
         "gpu_launches": args.steps,          # ONE kernel per step: fused assembly + PDIPM + wrench (pdipm_fast_kernel)
         "clocks": clocks,
     }

@@ -491,6 +491,20 @@ def test_host_entry_chunks_and_default_linearisation_point(pinned):
     h_x2 = pin(torch.zeros_like(h_x))
     ctx.solve_host(h_in2, h_rot, h_w2, num_calls=1, iters_per_call=5, x_out_host=h_x2)
     assert torch.equal(h_w2, h_w) and torch.equal(h_x2, h_x)
+    # bound call (buffers validated once): the tick a control loop runs after refilling the same buffers in place
+    tick = ctx.bind_host(h_in2, h_rot, h_w2, x_out_host=h_x2)
+    h_w2.zero_()
+    assert tick(1, 5) is h_w2 and torch.equal(h_w2, h_w)
+    inp3, rot3 = bp.workload.make_batch(B, seed=78)
+    for t, a in zip(h_in2, inp3):
+        if t is not None:
+            t.copy_(torch.as_tensor(a))
+    h_rot.copy_(torch.as_tensor(rot3, dtype=torch.float32))
+    tick(1, 5)
+    w3 = ctx.solve(_dev(inp3), torch.as_tensor(rot3, dtype=torch.float32, device=DEV), num_calls=1, iters_per_call=5)
+    assert torch.equal(h_w2, w3.cpu())
+    with pytest.raises(ValueError):
+        ctx.bind_host([t if i else t[:5] for i, t in enumerate(h_in)], h_rot, h_w)      # inconsistent batch sizes
     ctx.close()
 
 
