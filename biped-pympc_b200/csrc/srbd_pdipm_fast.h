@@ -271,6 +271,19 @@ struct PdipmFastT {
     double* f = fb();
     double* V = sm + SM::OFF_P;           // V_COUNT
     double* Wr = V + 232;                 // RW_COUNT
+    // x_ref (and the linearisation point, if given) are fetched before the value table is built: with the inputs in
+    // mapped host memory (host entry) their PCIe round trip then overlaps the table's
+    double xrv[4], xlv[4];
+    {
+      const double* xr = pa->qp_in[IN_XREF] + e * 120;
+      const double* xl = pa->qp_in[IN_X] ? pa->qp_in[IN_X] + e * 120 : nullptr;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int i = lane + 32 * m;
+        xrv[m] = i < 120 ? xr[i] : 0.0;
+        xlv[m] = (xl && i < 120) ? xl[i] : 1.0;
+      }
+    }
     qp_value_table(pa->qp_in, e, lane, 32, w, V, Wr);
     for (int i = lane; i < 168; i += 32) { const int rw = i / 14, c = i - 14 * rw; f[FB_B + i] = c < 12 ? V[V_NBD + 12 * rw + c] : 0.0; }
     if (lane < 12) { f[FB_AB + lane] = V[V_NEG1]; f[FB_HX + lane] = V[V_Q + lane]; f[FB_HU + lane] = V[V_R + lane]; }
@@ -285,12 +298,12 @@ struct PdipmFastT {
     }
     double* ws = gws();
     {   // f_x = grad - H z evaluated as the assembly kernel does (srbd_constraints.py:67-69)
-      const double* xr = pa->qp_in[IN_XREF] + e * 120;
-      const double* xl = pa->qp_in[IN_X] ? pa->qp_in[IN_X] + e * 120 : nullptr;
       int m12 = lane % 12;
-      for (int i = lane; i < 120; i += 32) {
-        const double xv = xl ? xl[i] : 1.0, q = V[V_Q + m12];
-        ws[FW_FX + i] = q * (xv - xr[i]) - q * xv;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int i = lane + 32 * m;
+        const double q = V[V_Q + m12];
+        if (i < 120) ws[FW_FX + i] = q * (xlv[m] - xrv[m]) - q * xlv[m];
         m12 += 8; if (m12 >= 12) m12 -= 12;
       }
     }

@@ -36,6 +36,25 @@ enum : int { RW_RB = 0, RW_IW = 9, RW_BODY = 18, RW_LF = 21, RW_RF = 24, RW_RL =
 // `lane` in [0, nl): nl cooperating lanes (32 = a whole warp per env, 16 = half a warp per env)
 SRBD_DEV void qp_value_table(const double* const* in, long long e, int lane0, int nl, const Warp& w, double* V, double* W) {
   // ---- stage raw inputs (nnz order = CasADi column-major) ---------------------------
+  if (nl == 32) {
+    // every load of the lane is issued before the first store: when the inputs are mapped host memory (host entry,
+    // read in place over PCIe) the env then pays one round trip, not one per input array
+    const int l = lane0;
+    double t_rb = 0, t_iw = 0, t_b0 = 0, t_b1 = 0, t_b2 = 0, t_b3 = 0, t_b4 = 0, t_x0 = 0, t_q = 0, t_r = 0, t_ct = 0, t_dt = 0, t_m = 0, t_mu = 0;
+    if (l < 9) { t_rb = in[IN_RBODY][e * 9 + l]; t_iw = in[IN_IWORLD][e * 9 + l]; }
+    if (l < 3) {
+      t_b0 = in[IN_BODY][e * 3 + l]; t_b1 = in[IN_LFOOT][e * 3 + l]; t_b2 = in[IN_RFOOT][e * 3 + l];
+      t_b3 = in[IN_RESLIN][e * 3 + l]; t_b4 = in[IN_RESANG][e * 3 + l];
+    }
+    if (l < 12) { t_x0 = in[IN_X0][e * 12 + l]; t_q = in[IN_Q][e * 12 + l]; t_r = in[IN_R][e * 12 + l]; }
+    if (l < 20) t_ct = in[IN_CONTACT][e * 20 + l];
+    if (l == 0) { t_dt = in[IN_DT][e]; t_m = in[IN_M][e]; t_mu = in[IN_MU][e]; }
+    if (l < 9) { W[RW_RB + l] = t_rb; W[RW_IW + l] = t_iw; }
+    if (l < 3) { W[RW_BODY + l] = t_b0; W[RW_LF + l] = t_b1; W[RW_RF + l] = t_b2; W[RW_RL + l] = t_b3; W[RW_RA + l] = t_b4; }
+    if (l < 12) { W[RW_X0 + l] = t_x0; V[V_Q + l] = t_q; V[V_R + l] = t_r; }
+    if (l < 20) W[RW_CT + l] = t_ct;
+    if (l == 0) { W[RW_DT] = t_dt; W[RW_M] = t_m; W[RW_MU] = t_mu; }
+  } else {
   for (int lane = lane0; lane < 9; lane += nl) { W[RW_RB + lane] = in[IN_RBODY][e * 9 + lane]; W[RW_IW + lane] = in[IN_IWORLD][e * 9 + lane]; }
   for (int lane = lane0; lane < 3; lane += nl) {
     W[RW_BODY + lane] = in[IN_BODY][e * 3 + lane];
@@ -52,6 +71,7 @@ SRBD_DEV void qp_value_table(const double* const* in, long long e, int lane0, in
   for (int lane = lane0; lane < 20; lane += nl) W[RW_CT + lane] = in[IN_CONTACT][e * 20 + lane];
   if (lane0 == 0) {
     W[RW_DT] = in[IN_DT][e]; W[RW_M] = in[IN_M][e]; W[RW_MU] = in[IN_MU][e];
+  }
   }
   w.sync();
   const double dt = W[RW_DT], m = W[RW_M], mu = W[RW_MU];
