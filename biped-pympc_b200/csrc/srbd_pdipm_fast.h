@@ -120,7 +120,7 @@ struct PdipmFastT {
   const PdipmArgs* pa;
   long long e;
   int lane, h, r, rr;
-  int prow[12];                 // packed offsets of row rr
+  int prow[12];                 // packed offsets of row rr, in BYTES of the block's precision (one add per access)
   int bs0, bs1;                 // sparse rows of column rr of Bbar
   double c0[4], c1[4];          // row rr of C = Abar diag(phix)  /  row rr of C'
   int i0[3], i1[3];             // their off-diagonal column indices
@@ -136,6 +136,12 @@ struct PdipmFastT {
   SRBD_DEV double* gws() const { return pa->work + e * (long long)pa->work_stride; }
 
   SRBD_DEV R* P(int k) const { return reinterpret_cast<R*>(sm + SM::OFF_P) + 78 * k; }
+  // entry (rr, m) of a packed block: base + byte offset (written as `Pm[prow[m]]` with element offsets the compiler forms
+  // (78 k + prow[m]) * 8 + base per access: two multiply-adds per element instead of one add)
+  template <class T> SRBD_DEV T& pe(T* Pm, int m) const {
+    using C = typename std::conditional<std::is_const<T>::value, const char, char>::type;
+    return *reinterpret_cast<T*>(reinterpret_cast<C*>(Pm) + prow[m]);
+  }
   SRBD_DEV double* fb() const { return sm + SM::OFF_FB; }
   SRBD_DEV double* bc() const { return sm + SM::OFF_BC + 24 * h; }
   SRBD_DEV double* tr() const { return sm + SM::OFF_TR + 32 * h; }
@@ -196,7 +202,7 @@ struct PdipmFastT {
     w.sync();
     // ---- per-lane registers ----------------------------------------------------------
 #pragma unroll
-    for (int m = 0; m < 12; ++m) prow[m] = pkf(rr, m);
+    for (int m = 0; m < 12; ++m) prow[m] = pkf(rr, m) * (int)sizeof(R);
     bs0 = 3 + rr % 3; bs1 = 9 + rr % 3;
     phx_rr = f[FB_PHX + rr];
     {
@@ -435,7 +441,7 @@ struct PdipmFastT {
     const R fk = (k == 0) ? (R)0 : (R)1;
     const R dg = (R)(phx_rr + IP_DELTA);
 #pragma unroll
-    for (int j = 0; j < 12; ++j) a[j] = fmaR(fk, (R)f[FB_SX + prow[j]], (rr == j) ? dg : (R)0);
+    for (int j = 0; j < 12; ++j) a[j] = fmaR(fk, (R)*reinterpret_cast<const double*>(reinterpret_cast<const char*>(f + FB_SX) + (kF32 ? 2 : 1) * prow[j]), (rr == j) ? dg : (R)0);
     w.sync();
     {
       R pl[12];
@@ -503,6 +509,21 @@ struct PdipmFastT {
   // pivot row p (one 8-byte store per lane instead of a 96-byte row).  The pivot row is scaled
   // immediately: keeping it unscaled with a deferred factor costs 100x in the residual
   // |P S - I| (measured), although the entrywise error is the same.
+  // one pivot step on the lane's row: the pivot lane takes the scaled pivot row from the published column (by symmetry
+  // entry c of the pivot row; bitwise what lane c computes as its t -- using the lane's own copy of the row instead costs
+  // a factor of 200 in the accuracy of dx, measured, and so does keeping the pivot row unscaled with a deferred factor),
+  // every other lane the rank-1 update.  A divergent branch: written as predicated PTX (@q mul / @!q fma) ptxas turns
+  // the pair into unconditional instructions plus four FSELs per entry (84 instead of 47 instructions per pivot step).
+  SRBD_DEV void sweep_update(R a[12], const R bv[12], R di, R t, bool piv, int p) const {
+    if (piv) {
+#pragma unroll
+      for (int c = 0; c < 12; ++c) if (c != p) a[c] = bv[c] * di;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 12; ++c) if (c != p) a[c] = fmaR(-t, bv[c], a[c]);
+    }
+  }
+
   SRBD_DEV void sweep_invert(R a[12]) const {
     R* b = bcr();
     w.sync();   // the broadcast scratch still holds form_row's exchange
@@ -516,13 +537,7 @@ struct PdipmFastT {
       const R di = rcp(bv[p]);
       const bool piv = (rr == p);
       const R t = a[p] * di;
-      if (piv) {
-#pragma unroll
-        for (int c = 0; c < 12; ++c) if (c != p) a[c] = bv[c] * di;
-      } else {
-#pragma unroll
-        for (int c = 0; c < 12; ++c) if (c != p) a[c] = fmaR(-t, bv[c], a[c]);
-      }
+      sweep_update(a, bv, di, t, piv, p);
       a[p] = piv ? -di : t;
     }
 #pragma unroll
@@ -547,19 +562,19 @@ struct PdipmFastT {
       else {
         const R* P5 = P(5);
 #pragma unroll
-        for (int c = 0; c < 12; ++c) n[c] = P5[prow[c]];
+        for (int c = 0; c < 12; ++c) n[c] = pe(P5, c);
       }
       if (t > 0) {
         R o[12];
         const R* Pn = P((t == 5) ? 4 : (h ? k + 1 : k - 1));
 #pragma unroll
-        for (int c = 0; c < 12; ++c) o[c] = Pn[prow[c]];
+        for (int c = 0; c < 12; ++c) o[c] = pe(Pn, c);
         couple(n, o, pr(h), h);
       }
       if (t == 4 && h == 1) {
         R* P5 = P(5);
 #pragma unroll
-        for (int c = 0; c < 12; ++c) if (c <= rr) P5[prow[c]] = n[c];
+        for (int c = 0; c < 12; ++c) if (c <= rr) pe(P5, c) = n[c];
       }
       sweep_invert(n);
       if (fwd && t < 5) {
@@ -585,7 +600,7 @@ struct PdipmFastT {
       if (act) {
         R* Pk = P(k);
 #pragma unroll
-        for (int c = 0; c < 12; ++c) if (c <= rr) Pk[prow[c]] = n[c];
+        for (int c = 0; c < 12; ++c) if (c <= rr) pe(Pk, c) = n[c];
         const int slot = h ? rr : rr - 6;
         if (slot >= 0 && slot < 6) st12(pr(h) + 12 * slot, n);
       }
@@ -602,7 +617,7 @@ struct PdipmFastT {
     double q0 = 0.0, q1 = 0.0, q2 = 0.0;
 #pragma unroll
     for (int m = 0; m < 12; m += 3) {
-      q0 = fma((double)Pm[prow[m]], v[m], q0); q1 = fma((double)Pm[prow[m + 1]], v[m + 1], q1); q2 = fma((double)Pm[prow[m + 2]], v[m + 2], q2);
+      q0 = fma((double)pe(Pm, m), v[m], q0); q1 = fma((double)pe(Pm, m + 1), v[m + 1], q1); q2 = fma((double)pe(Pm, m + 2), v[m + 2], q2);
     }
     return q0 + q1 + q2;
   }
