@@ -81,16 +81,17 @@ struct PdipmSmem {
 
 #if defined(__CUDACC__) && !defined(SRBD_HOST_EMUL)
 typedef double2 dbl2;
-// 1/x to ~1 ulp: 20-bit seed + two Newton steps (no slow-path call, unlike the IEEE division)
+// 1/x to ~1 ulp: 20-bit seed + one cubic step (no slow-path call, unlike the IEEE division)
 SRBD_DEV double rcp(double x) {
 #ifdef SRBD_IEEE_DIV
   return 1.0 / x;
 #endif
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  // one third-order step e <- e + e^2 (2^-20 -> 2^-60): three dependent FMAs.  Two Newton steps (four FMAs) are not more
+  // accurate after rounding and sit on the critical path of every pivot step of the sweep (measured: -0.7 %)
   double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
+  e = fma(e, e, e);
   return fma(y, e, y);
 }
 #else

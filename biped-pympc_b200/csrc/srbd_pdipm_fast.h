@@ -624,46 +624,59 @@ struct PdipmFastT {
   SRBD_DEV void solve_thomas(bool fwd_done = false) {
     double* vy = sm + SM::OFF_VY;
     double* b = bc();
-    // forward: t_k -= M (P_nb t_nb).  t = 4: the bottom half applies C_6' (from 6) to block 5,
-    // t = 5: the top half applies C_5 (from 4).  fwd_done: factor(true) has already done it
-#pragma unroll 1
-    for (int t = fwd_done ? 6 : 1; t < 6; ++t) {
-      int k, nb;
-      if (t < 4) { k = h ? 9 - t : t; nb = h ? k + 1 : k - 1; }
-      else if (t == 4) { k = h ? 5 : 4; nb = h ? 6 : 3; }
-      else { k = 5; nb = 4; }
-      const bool act = (t < 5) || (h == 0);
-      double tv[12];
-      ld12(vy + 12 * nb, tv);
-      b[rr] = prow_dot(P(nb), tv);
-      w.sync();
+    // The blocks are walked with per-lane strides (top half: towards stage 5 from 0, bottom half: from 9) instead of
+    // recomputing k, its neighbour and the activity flags from t in every trip; the coupling rows of the direction are
+    // selected once per loop, not once per use.
+    const int dk = h ? -1 : 1;
+    // forward: t_k -= M (P_nb t_nb), nb -> k = nb + dk: top 0->1 ... 3->4, 4->5 ; bottom 9->8 ... 6->5, then idle (its
+    // trip 5 recomputes 5->4 without storing).  fwd_done: factor(true) has already done it
+    if (!fwd_done) {
       const double cv0 = h ? c1[0] : c0[0], cv1 = h ? c1[1] : c0[1], cv2 = h ? c1[2] : c0[2], cv3 = h ? c1[3] : c0[3];
       const int j1 = h ? i1[0] : i0[0], j2 = h ? i1[1] : i0[1], j3 = h ? i1[2] : i0[2];
-      const double d = cv0 * b[rr] + cv1 * b[j1] + cv2 * b[j2] + cv3 * b[j3];
-      if (act && r < 12) vy[12 * k + rr] -= d;
-      w.sync();
-    }
-    // backward: dy_5 ; then 4|6 ; 3|7 ; 2|8 ; 1|9 ; 0|-   (top uses C_{k+1}', bottom uses C_k)
+      double* vnb = vy + (h ? 108 : 0);
+      const R* Pnb = P(h ? 9 : 0);
 #pragma unroll 1
-    for (int t = 0; t < 6; ++t) {
-      int k = (t == 0) ? 5 : (h ? 5 + t : 5 - t);
-      const bool act = (t == 0) ? (h == 0) : (k <= 9);
-      if (k > 9) k = 9;
-      double tk = vy[12 * k + rr];
-      if (t > 0) {
-        const double* yn = vy + 12 * (h ? k - 1 : k + 1);
-        // top: C_{k+1}' (type 1) ; bottom: C_k (type 0)
-        const double cv0 = h ? c0[0] : c1[0], cv1 = h ? c0[1] : c1[1], cv2 = h ? c0[2] : c1[2], cv3 = h ? c0[3] : c1[3];
-        const int j1 = h ? i0[0] : i1[0], j2 = h ? i0[1] : i1[1], j3 = h ? i0[2] : i1[2];
-        tk -= cv0 * yn[rr] + cv1 * yn[j1] + cv2 * yn[j2] + cv3 * yn[j3];
+      for (int t = 1; t < 6; ++t) {
+        const bool act = (t < 5) || (h == 0);
+        double tv[12];
+        ld12(vnb, tv);
+        b[rr] = prow_dot(Pnb, tv);
+        w.sync();
+        const double d = cv0 * b[rr] + cv1 * b[j1] + cv2 * b[j2] + cv3 * b[j3];
+        vnb += 12 * dk; Pnb += 78 * dk;
+        if (act && r < 12) vnb[rr] -= d;
+        w.sync();
       }
-      b[rr] = tk;
-      w.sync();
-      double bv[12];
-      ld12(b, bv);
-      const double dy = prow_dot(P(k), bv);
-      if (act && r < 12) vy[12 * k + rr] = dy;
-      w.sync();
+    }
+    // backward: dy_5 ; then 4|6 ; 3|7 ; 2|8 ; 1|9 ; 0|-   (top uses C_{k+1}' (type 1), bottom uses C_k (type 0))
+    {
+      const double cv0 = h ? c0[0] : c1[0], cv1 = h ? c0[1] : c1[1], cv2 = h ? c0[2] : c1[2], cv3 = h ? c0[3] : c1[3];
+      const int j1 = h ? i0[0] : i1[0], j2 = h ? i0[1] : i1[1], j3 = h ? i0[2] : i1[2];
+      double* vk = vy + 60;
+      const R* Pk = P(5);
+      {
+        b[rr] = vk[rr];
+        w.sync();
+        double bv[12];
+        ld12(b, bv);
+        const double dy = prow_dot(Pk, bv);
+        if (h == 0 && r < 12) vk[rr] = dy;
+        w.sync();
+      }
+#pragma unroll 1
+      for (int t = 1; t < 6; ++t) {
+        const double* yn = vk;                  // the block solved in the previous trip
+        const bool act = (t < 5) || (h == 0);   // the bottom half has no sixth block
+        if (act) { vk -= 12 * dk; Pk -= 78 * dk; }
+        const double tk = vk[rr] - (cv0 * yn[rr] + cv1 * yn[j1] + cv2 * yn[j2] + cv3 * yn[j3]);
+        b[rr] = tk;
+        w.sync();
+        double bv[12];
+        ld12(b, bv);
+        const double dy = prow_dot(Pk, bv);
+        if (act && r < 12) vk[rr] = dy;
+        w.sync();
+      }
     }
   }
 
