@@ -61,8 +61,11 @@ struct FastSmem {
 enum : int { FW_DX = 0, FW_DY = 240, FW_S = 380, FW_Z = 540, FW_Q = 700,
              // fused tick only: f of the states, c_d | c_d + A_d x0, F_max * contact
              FW_FX = 860, FW_CD = 980, FW_FC = 1004,
+             // working copies of s, z and the bound h of the lane's rows: with ds, dz and D/W above they are addressed
+             // as one per-row pointer + immediate (the caller's s / z buffers are read once and written once per call)
+             FW_SV = 1024, FW_ZV = 1184, FW_H = 1344,
              // fp32 pivot blocks with refinement only: re of the iteration (r4 of the affine solve), the unrefined dx
-             FW_RE = 1024, FW_RX = 1152, FW_END = 1392 };
+             FW_RE = 1504, FW_RX = 1632, FW_END = 1872 };
 static_assert(FW_END <= PDIPM_WORK_DOUBLES_FAST, "work buffer too small");
 
 // Packed storage of the symmetric 12x12 blocks (P_k, A phix A'): row i keeps its entries (i, 0..i) contiguous, as in the
@@ -791,6 +794,15 @@ struct PdipmFastT {
         }
       }
       w.sync();
+      {
+        double* ws = gws();
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+          const int k = h ? 9 - t : t, j = 16 * k + r;
+          double* row = ws + j;
+          row[FW_SV] = oS[j]; row[FW_ZV] = oZ[j]; row[FW_H] = h_of(k, j);
+        }
+      }
     }
 
     double* vx = sm + SM::OFF_VX;
@@ -848,12 +860,11 @@ struct PdipmFastT {
 #ifdef SRBD_HOST_EMUL
           a_pri_aff = ap; a_dual_aff = ad;
 #endif
-          const double* oS = gout(IPO_S, NINEQ); const double* oZ = gout(IPO_Z, NINEQ);
           double a_mu = 0.0;
 #pragma unroll
           for (int t = 0; t < 5; ++t) {
-            const int j = 16 * (h ? 9 - t : t) + r;
-            a_mu = fma(fma(ap, ws[FW_S + j], oS[j]), fma(ad, ws[FW_Z + j], oZ[j]), a_mu);
+            const double* row = ws + 16 * (h ? 9 - t : t) + r;
+            a_mu = fma(fma(ap, row[FW_S], row[FW_SV]), fma(ad, row[FW_Z], row[FW_ZV]), a_mu);
           }
           const double mu_aff = warp_sum(a_mu) / (double)NINEQ;
           const double sg = mu_aff * rcp(mu);
@@ -872,7 +883,7 @@ struct PdipmFastT {
       // ======================= update ====================================================
       {
         double* ws = gws();
-        double* oX = gout(IPO_X, NZ); double* oS = gout(IPO_S, NINEQ); double* oZ = gout(IPO_Z, NINEQ); double* oY = gout(IPO_Y, NEQ);
+        double* oX = gout(IPO_X, NZ); double* oY = gout(IPO_Y, NEQ);
         double a_new = 0.0;
         {   // all global loads of a lane are issued before the first dependent use (L2 latency once)
           double xa[8], xo[8], ya[5], yo[5];
@@ -887,16 +898,25 @@ struct PdipmFastT {
         }
 #pragma unroll
         for (int t = 0; t < 5; ++t) {
-          const int j = 16 * (h ? 9 - t : t) + r;
-          const double sn = fmax(fma(a_pri, ws[FW_S + j], oS[j]), 1e-8);
-          const double zn = fmax(fma(a_dual, ws[FW_Z + j], oZ[j]), 1e-8);
-          oS[j] = sn; oZ[j] = zn;
+          double* row = ws + 16 * (h ? 9 - t : t) + r;
+          const double sn = fmax(fma(a_pri, row[FW_S], row[FW_SV]), 1e-8);
+          const double zn = fmax(fma(a_dual, row[FW_Z], row[FW_ZV]), 1e-8);
+          row[FW_SV] = sn; row[FW_ZV] = zn;
           a_new = fma(sn, zn, a_new);
         }
         mu_new = warp_sum(a_new) / (double)NINEQ;
       }
       w.sync();
       if (A.tol > 0.0 && n_rx < A.tol && n_rs < A.tol && n_re < A.tol && mu_new < A.tol) { ++it; break; }
+    }
+    {   // s, z of the lane's rows back to the caller's buffers
+      const double* ws = gws();
+      double* oS = gout(IPO_S, NINEQ); double* oZ = gout(IPO_Z, NINEQ);
+#pragma unroll
+      for (int t = 0; t < 5; ++t) {
+        const int j = 16 * (h ? 9 - t : t) + r;
+        oS[j] = ws[FW_SV + j]; oZ[j] = ws[FW_ZV + j];
+      }
     }
     if (lane == 0) {
       double* oRes = gout(IPO_RES, 4);
@@ -918,7 +938,6 @@ struct PdipmFastT {
     double* sx = sm + SM::OFF_P;         // iterate scratch (phase A only): x | y | (hx + beta) x
     double* sy = sx + 240; double* xs = sx + 380;
     double* ws = gws();
-    const double* oS = gout(IPO_S, NINEQ); const double* oZ = gout(IPO_Z, NINEQ);
     const bool fused = pa->fused != 0;
     const double* gF = gin(IP_F, NZ); const double* gB = gin(IP_B, NEQ);
     {
@@ -949,7 +968,8 @@ struct PdipmFastT {
     for (int t = 0; t < 5; ++t) {
       const int k = h ? 9 - t : t;
       const int j = 16 * k + r;
-      const double sv = oS[j], zv = oZ[j], hv = h_of(k, j);
+      double* row = ws + j;
+      const double sv = row[FW_SV], zv = row[FW_ZV], hv = row[FW_H];
       double fu = 0.0, fxv, bd, bm = 0.0;           // fused: f_u = 0, b_mx = 0 by construction
       if (fused) { fxv = ws[FW_FX + 12 * k + rr]; bd = ws[FW_CD + (k == 0 ? 12 : 0) + rr]; }
       else {
@@ -968,7 +988,7 @@ struct PdipmFastT {
         const double q = rcp(fma(IP_DELTA, W, 1.0));     // D / W
         const double D = W * q;
         const double Dg = fma(D, rs, -(q * zv));         // D (r2 / W - r3), r2 = -z, r3 = -rs
-        ws[FW_S + j] = fma(IP_DELTA, Dg, -rs); ws[FW_Z + j] = Dg; ws[FW_Q + j] = q;
+        row[FW_S] = fma(IP_DELTA, Dg, -rs); row[FW_Z] = Dg; row[FW_Q] = q;
         Dsm[j] = D;
         gdg = gather_rows(Dg, ga, gb); gz = gather_rows(zv, ga, gb);
         a_sz = fma(sv, zv, a_sz); a_rs = fma(rs, rs, a_rs);
@@ -1036,13 +1056,11 @@ struct PdipmFastT {
   // r2 = -(s z + ds_aff dz_aff - sigma mu) / s ; leaves -G' D g in the input part of vx
   SRBD_DEV void corrector_rhs(int k, double smu) const {
     double* vx = sm + SM::OFF_VX;
-    double* ws = gws();
-    const double* oS = gout(IPO_S, NINEQ); const double* oZ = gout(IPO_Z, NINEQ);
-    const int j = 16 * k + r;
-    const double sv = oS[j], zv = oZ[j], dsa = ws[FW_S + j], dza = ws[FW_Z + j], q = ws[FW_Q + j];
+    double* row = gws() + 16 * k + r;
+    const double sv = row[FW_SV], zv = row[FW_ZV], dsa = row[FW_S], dza = row[FW_Z], q = row[FW_Q];
     const double r2 = -(rcp(sv) * (sv * zv + dsa * dza - smu));
     const double Dg = q * r2;
-    ws[FW_S + j] = fma(IP_DELTA, Dg, dsa); ws[FW_Z + j] = dza + Dg;
+    row[FW_S] = fma(IP_DELTA, Dg, dsa); row[FW_Z] = dza + Dg;
     vx[120 + 12 * k + rr] = -gather_rows(Dg, fb()[goa], fb()[gob]);
     w.sync();
   }
@@ -1104,10 +1122,9 @@ struct PdipmFastT {
     const double* f = fb();
     double* vx = sm + SM::OFF_VX;
     double* vy = sm + SM::OFF_VY;
-    double* ws = gws();
-    const double* oS = gout(IPO_S, NINEQ); const double* oZ = gout(IPO_Z, NINEQ);
     const int j = 16 * k + r;
-    const double sv = oS[j], zv = oZ[j], sS = ws[FW_S + j], sZ = ws[FW_Z + j];
+    double* row = gws() + j;
+    const double sv = row[FW_SV], zv = row[FW_ZV], sS = row[FW_S], sZ = row[FW_Z];
     double* b = bc();
     double* vu = vx + 120 + 12 * k;
     const double* dyk = vy + 12 * k;
@@ -1134,7 +1151,7 @@ struct PdipmFastT {
       const double Dg = sm[SM::OFF_D + j] * gdu;
       const double dz = sZ + Dg;
       const double ds = fma(IP_DELTA, Dg, sS - gdu);
-      ws[FW_S + j] = ds; ws[FW_Z + j] = dz;       // affine (pass 0) / combined (pass 1)
+      row[FW_S] = ds; row[FW_Z] = dz;       // affine (pass 0) / combined (pass 1)
       mn_s = fmin(mn_s, ratio(sv, ds));
       mn_z = fmin(mn_z, ratio(zv, dz));
     }
