@@ -475,7 +475,7 @@ struct PdipmFastT {
     }
   }
 
-  // n -= M P M' with M the coupling of `type`; own = row rr of P, hand = handed-over rows
+  // n -= M P M' = n + M N M' with M the coupling of `type`; own = row rr of N = -P, hand = handed-over rows of N
   SRBD_DEV void couple(R n[12], const R own[12], const R* hand, int type) const {
     const R cv0 = (R)(type ? c1[0] : c0[0]), cv1 = (R)(type ? c1[1] : c0[1]);
     const R cv2 = (R)(type ? c1[2] : c0[2]), cv3 = (R)(type ? c1[3] : c0[3]);
@@ -503,12 +503,14 @@ struct PdipmFastT {
       else if (cc < 6) o += U[cc + 6] * (R)cm[21 + cc - 3];
       else if (cc < 9) o += U[0] * (R)cm[24 + 3 * (cc - 6)] + U[1] * (R)cm[24 + 3 * (cc - 6) + 1] + U[2] * (R)cm[24 + 3 * (cc - 6) + 2];
       else o += U[cc - 6] * (R)cm[33 + cc - 9];
-      n[cc] -= o;
+      n[cc] += o;
     }
   }
 
-  // symmetric sweep on all 12 pivots of the SPD block whose row rr is a[]; returns row rr of its
-  // inverse.  Lane c publishes its entry of pivot column p, which by symmetry is entry c of
+  // symmetric sweep on all 12 pivots of the SPD block whose row rr is a[]; returns row rr of the NEGATED
+  // inverse, which is what sweeping all pivots yields: every consumer (the packed blocks P_k, the hand-over window, the
+  // mat-vecs, the couplings) works with N_k = -P_k and flips the sign in an FMA operand for free instead of spending
+  // twelve negations per block here.  Lane c publishes its entry of pivot column p, which by symmetry is entry c of
   // pivot row p (one 8-byte store per lane instead of a 96-byte row).  The pivot row is scaled
   // immediately: keeping it unscaled with a deferred factor costs 100x in the residual
   // |P S - I| (measured), although the entrywise error is the same.
@@ -517,6 +519,8 @@ struct PdipmFastT {
   // a factor of 200 in the accuracy of dx, measured, and so does keeping the pivot row unscaled with a deferred factor),
   // every other lane the rank-1 update.  A divergent branch: written as predicated PTX (@q mul / @!q fma) ptxas turns
   // the pair into unconditional instructions plus four FSELs per entry (84 instead of 47 instructions per pivot step).
+  // (a[p] is set outside the branch with a select: written as `if (rr == p) a[p] = -di` in all twelve unrolled steps the
+  //  compiler recognises a[rr], indexes the row dynamically and moves it to local memory: 2.4x slower, measured)
   SRBD_DEV void sweep_update(R a[12], const R bv[12], R di, R t, bool piv, int p) const {
     if (piv) {
 #pragma unroll
@@ -543,8 +547,6 @@ struct PdipmFastT {
       sweep_update(a, bv, di, t, piv, p);
       a[p] = piv ? -di : t;
     }
-#pragma unroll
-    for (int c = 0; c < 12; ++c) a[c] = -a[c];
   }
 
   // fwd: the forward substitution of the affine solve (t_next -= M (P_k t_k), solve_thomas) is done here, at the end of
@@ -586,7 +588,7 @@ struct PdipmFastT {
         double q0 = 0.0, q1 = 0.0, q2 = 0.0;
 #pragma unroll
         for (int m = 0; m < 12; m += 3) {
-          q0 = fma((double)n[m], tv[m], q0); q1 = fma((double)n[m + 1], tv[m + 1], q1); q2 = fma((double)n[m + 2], tv[m + 2], q2);
+          q0 = fma(-(double)n[m], tv[m], q0); q1 = fma(-(double)n[m + 1], tv[m + 1], q1); q2 = fma(-(double)n[m + 2], tv[m + 2], q2);
         }
         double* b = bc();
         // fp64: the sweep's last pivot row sits in the second half of the scratch, slots 0..11 are free; the fp32 sweep's
@@ -614,13 +616,13 @@ struct PdipmFastT {
   // ------------------------------------------------------------------------------------
   // block-Thomas solve on vy[0..119]  (rho -> t -> dy), twisted
   // ------------------------------------------------------------------------------------
-  // row rr of a packed pivot-block inverse times the 12-vector v (fp32 blocks: the stored entries are widened, the
+  // row rr of a pivot-block inverse (stored negated, packed) times the 12-vector v (fp32 blocks: the stored entries are widened, the
   // products and sums are fp64 -- with fp32 products the refined mode stops at 2e-4 instead of 1e-5)
   SRBD_DEV double prow_dot(const R* Pm, const double v[12]) const {
     double q0 = 0.0, q1 = 0.0, q2 = 0.0;
 #pragma unroll
     for (int m = 0; m < 12; m += 3) {
-      q0 = fma((double)pe(Pm, m), v[m], q0); q1 = fma((double)pe(Pm, m + 1), v[m + 1], q1); q2 = fma((double)pe(Pm, m + 2), v[m + 2], q2);
+      q0 = fma(-(double)pe(Pm, m), v[m], q0); q1 = fma(-(double)pe(Pm, m + 1), v[m + 1], q1); q2 = fma(-(double)pe(Pm, m + 2), v[m + 2], q2);
     }
     return q0 + q1 + q2;
   }
