@@ -106,7 +106,7 @@ def cpu_reference_run(n_envs, iters, steps, warmup, threads, seed=20261018, want
     """Times the reference's CPU path on the workload.  want="reference": oracle/_ref/lib<fn>_cpu*.so, the expression tapes
     of the reference's two functions (built from its sources by oracle/make_cusadi_ref.py) compiled to C and run with
     `omp parallel for` over envs, the reference's own CPU convention (evaluate_parallel_cpu.cpp:79-82; gcc -O3
-    -march=native like run_benchmarks.py:46 where the compiler finishes, else the -O1 build) -- kind "reference".
+    -march=x86-64-v3 -- run_benchmarks.py:46 uses -O3 -march=native -- where that build exists, else the -O1 build) -- kind "reference".
     want="port" (or no oracle/_ref): the C restatement oracle/srbd_oracle.c (literal qp_former + full-KKT sparse LDL^T
     PDIPM, gcc -O3 -march=native, OpenMP over envs) -- kind "port".
     Returns (solves/s, per-step seconds, kind, description)."""

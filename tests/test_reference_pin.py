@@ -277,7 +277,7 @@ def test_compiled_tapes_of_the_reference_functions_reproduce_the_fixture(ref):
     -- linearised with work-slot reuse, the view the reference's CUDA generator walks -- compiled to C.  Same graph, same
     IEEE operations: bit-identical to the graph evaluation that produced the fixture."""
     import cusadi_ref
-    if not cusadi_ref.cpu_available():
+    if not cusadi_ref.cpu_available(prefer_o3=False):
         pytest.skip("oracle/_ref/lib*_cpu.so not built (python oracle/make_cusadi_ref.py --target cpu)")
     cpu = cusadi_ref.CusadiRefCpu(prefer_o3=False)     # the -O1 build: no FMA contraction, bit-identical to the fixture
     qp = cpu.qp_former(_inputs(ref))
