@@ -204,8 +204,10 @@ struct PdipmFastT {
     }
     w.sync();
     // ---- per-lane registers ----------------------------------------------------------
+    // (the lane's own row start is looked up once: kRow[] with a run-time index is a chain of selects)
+    const int myrow = pkf_row(rr);
 #pragma unroll
-    for (int m = 0; m < 12; ++m) prow[m] = pkf(rr, m) * (int)sizeof(R);
+    for (int m = 0; m < 12; ++m) prow[m] = (m <= rr ? myrow + m : pkf_row(m) + rr) * (int)sizeof(R);
     bs0 = 3 + rr % 3; bs1 = 9 + rr % 3;
     phx_rr = f[FB_PHX + rr];
     {
@@ -244,7 +246,7 @@ struct PdipmFastT {
         double acc = c0[0] * PdipmWarp<true>::abar(A, j, q);
 #pragma unroll
         for (int a = 0; a < 3; ++a) acc += c0[1 + a] * PdipmWarp<true>::abar(A, j, i0[a]);
-        f[FB_SX + pkf(q, j)] = acc;
+        f[FB_SX + myrow + j] = acc;     // pkf(q, j) for j <= q: the lane's own row is contiguous
       }
     }
     {   // inequality row r
@@ -705,7 +707,11 @@ struct PdipmFastT {
   // ------------------------------------------------------------------------------------
   SRBD_DEV int run(const PdipmArgs& A, long long env) {
     pa = &A; e = env;
-    lane = w.lane(); h = lane >> 4; r = lane & 15; rr = r < 12 ? r : 11;
+    lane = w.lane();
+#if defined(__CUDACC__) && !defined(SRBD_HOST_EMUL)
+    asm volatile("" : "+r"(lane));   // keep it in a register: the compiler otherwise re-reads the special register all over
+#endif
+    h = lane >> 4; r = lane & 15; rr = r < 12 ? r : 11;
     {
       double* oX = gout(IPO_X, NZ); double* oS = gout(IPO_S, NINEQ); double* oZ = gout(IPO_Z, NINEQ); double* oY = gout(IPO_Y, NEQ);
       const bool warm = A.cold_start && A.warm_xy && !(A.reset && A.reset[e] != 0);
