@@ -299,6 +299,51 @@ def sub_converge(bp, torch, dev, local_rank, flush, steps=3):
             "what": "BASELINE configs[3]: run to convergence, beyond the reference's 5-iteration codegen limit"}
 
 
+def sub_single_env(bp, torch, dev, local_rank, reps=200):
+    """BASELINE configs[0]: the single T1 standing problem, batch = 1 (the reference's CPU-runnable case): latency of one
+    solve on the GPU (one warp of one SM) next to the reference's own tape on one host core."""
+    inp = bp.workload.config1_t1_standing()
+    ins = [torch.as_tensor(a, device=dev) for a in inp]
+    rot_t = torch.eye(3, dtype=torch.float32, device=dev).reshape(1, 3, 3).contiguous()
+    ctx = bp.Context(1, local_rank)
+    for _ in range(20):
+        ctx.solve(ins, rot_t, num_calls=1, iters_per_call=ITERS)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in ev:
+        a.record()
+        ctx.solve(ins, rot_t, num_calls=1, iters_per_call=ITERS)
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    t0 = time.perf_counter()
+    for _ in range(50):
+        ctx.solve(ins, rot_t, num_calls=1, iters_per_call=ITERS)
+        torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / 50
+    ctx.close()
+    out = {"envs": 1, "iters": ITERS, "gpu_ms": {"p50": ts[len(ts) // 2], "p99": ts[int(0.99 * (len(ts) - 1))]},
+           "gpu_call_plus_sync_wall_ms": 1e3 * wall,
+           "what": "BASELINE configs[0]: single T1 biped standing problem, horizon 10, 5 PDIPM iterations, batch = 1 (CUDA events "
+                   "around one call / wall clock of call + synchronize)"}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import cusadi_ref
+        if cusadi_ref.cpu_available():
+            cpu = cusadi_ref.CusadiRefCpu()
+            for _ in range(3):
+                cpu.pdipm5(cpu.qp_former(inp, 1), threads=1)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                cpu.pdipm5(cpu.qp_former(inp, 1), threads=1)
+            out["cpu_reference_tape_ms"] = 1e3 * (time.perf_counter() - t0) / 20
+            out["cpu_flags"] = cpu.flags
+    except Exception as exc:
+        out["cpu_reference_tape_ms"] = None
+        out["cpu_error"] = repr(exc)
+    return out
+
+
 def sub_fp32_mode(bp, torch, dev, local_rank, flush, ref_ms, steps=10):
     """north_star's optional fp32 mode (include/srbd_mpc.h SRBD_F32_FACTOR / _REFINE / _REFINE2), measured on the metric's
     4 096-env workload: time of the fused tick per mode and the worst per-env relative error of x after the 5 iterations
@@ -793,7 +838,8 @@ def run_b200(args):
                         "h2d_bytes_per_step": sum(a.numel() * 8 for a in hi) + hr.numel() * 4, "d2h_bytes_per_step": hw.numel() * 4}
             line["e2e_all17_pinned"] = e2e_case(True)
             line["e2e_all17_pageable"] = e2e_case(False)
-            for key, fn in (("fp32_mode", lambda: sub_fp32_mode(bp, torch, dev, local_rank, flush, line["ms_per_step"])),
+            for key, fn in (("single_env_config0", lambda: sub_single_env(bp, torch, dev, local_rank)),
+                            ("fp32_mode", lambda: sub_fp32_mode(bp, torch, dev, local_rank, flush, line["ms_per_step"])),
                             ("converge_16384", lambda: sub_converge(bp, torch, dev, local_rank, flush)),
                             ("closed_loop_4096x1000", sub_closed_loop),
                             ("compat_dropin", lambda: run_compat(argparse.Namespace(envs=B), emit=False))):
