@@ -16,7 +16,8 @@
 //     of being re-gathered from the packed storage;
 //   * the per-inequality-row data (s, z, the two direction slots, D w^-1) is lane-private and
 //     lives in the L2-resident work buffer; only D stays in shared memory;
-//   * 2 066 doubles of shared memory per warp -> 14 warps (environments) per SM.
+//   * 2 068 doubles of shared memory per warp -> 14 warps (environments) per SM; the lanes' rows of the pivot-block
+//     inverses in tensor memory (fp64 path).
 //
 // Compiled for the GPU (srbd_pdipm.cu) and, for tests only, for the host under the warp
 // emulator of srbd_warp.h.
@@ -55,7 +56,9 @@ struct FastSmem {
   static constexpr int OFF_PR = 1348;      // ... or (factor only) 2 x 72 handed-over rows of P
   static constexpr int OFF_D = 1492;       // 160
   static constexpr int OFF_FB = 1652;
-  static constexpr int SIZE = OFF_FB + FB_SIZE;   // 2066
+  static constexpr int OFF_TM = OFF_FB + FB_SIZE;   // 32-bit tensor-memory address of the warp's slot 0 (re-read at every
+                                                    // use: a register held across the whole solve costs spills)
+  static constexpr int SIZE = OFF_TM + 2;           // 2068 (even: every warp's region stays 16-byte aligned)
 };
 // lane-private per-row scratch in the work buffer
 enum : int { FW_DX = 0, FW_DY = 240, FW_S = 380, FW_Z = 540, FW_Q = 700,
@@ -133,6 +136,74 @@ struct PdipmFastT {
   int doff, moff;               // fb offsets of its constant Psi diagonal / 1/mx_den (or of a zero)
   int g_src;                    // lane that ends up with sum_j G[j, rr] v_j in gather_rows (-1: the column has no rows)
   enum : int { FB_ZERO = FB_B + 12 };   // a structurally zero slot (pad column of Bbar)
+
+  // ---- the lane's rows of the pivot-block inverses live in TENSOR MEMORY (fp64 path) ---------------------------------
+  // A lane only ever needs ITS OWN row of N_k = -P_k of the blocks its half-warp eliminated (mat-vecs of the block
+  // solves, own row in the coupling): lane-private data, which the shared-memory pipe -- the resource that binds this
+  // kernel -- serves worst (packed symmetric storage: twelve 8-byte loads with twelve different addresses per half-warp
+  // and an address computation each).  Blackwell's tensor memory is 128 lanes x 512 32-bit columns per SM with its own
+  // datapath: tcgen05.st / tcgen05.ld move N consecutive columns of every lane of a warp's 32-lane sub-partition in ONE
+  // instruction (measured, tools/tmem_probe.cu: a 12-double row per lane out and back in 234 cycles with 14 warps per SM,
+  // 1 299 cycles through shared memory).  Warp w owns lanes 32 (w % 4) .. +31 and columns 128 (w / 4) .. +119: five slots
+  // of 24 columns; slot t holds the row of the block the lane's half eliminated in round t (top half: block t, bottom
+  // half: block 9 - t), so both halves address the same columns in every phase.  Block 5 (the merge block) stays packed
+  // in shared memory.  The fp32 mode and the host emulator keep the slots in ordinary memory.
+  static constexpr bool kTm = !kF32;
+#if defined(__CUDACC__) && !defined(SRBD_HOST_EMUL)
+  // tensor-memory address of slot 0 of this warp (lane field = its sub-partition), written by the kernel before run()
+  SRBD_DEV unsigned tm_base() const { return *reinterpret_cast<const volatile unsigned*>(sm + SM::OFF_TM); }
+  SRBD_DEV void tm_st(int slot, const double v[12]) const {
+    const unsigned addr = tm_base() + 24u * (unsigned)slot;
+    unsigned q[24];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { q[2 * i] = (unsigned)__double2loint(v[i]); q[2 * i + 1] = (unsigned)__double2hiint(v[i]); }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(addr), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]), "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7]),
+                    "r"(q[8]), "r"(q[9]), "r"(q[10]), "r"(q[11]), "r"(q[12]), "r"(q[13]), "r"(q[14]), "r"(q[15]) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(addr + 16u), "r"(q[16]), "r"(q[17]), "r"(q[18]), "r"(q[19]), "r"(q[20]), "r"(q[21]), "r"(q[22]), "r"(q[23]) : "memory");
+  }
+  // the load is issued early (its latency then hides behind the exchange of the right-hand side) and completed by
+  // tm_ld_finish right before the first use; stores are only waited for when the next load is issued
+  SRBD_DEV void tm_ld_issue(int slot, unsigned q[24]) const {
+    const unsigned addr = tm_base() + 24u * (unsigned)slot;
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]),
+                   "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]) : "r"(addr) : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(q[16]), "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]) : "r"(addr + 16u) : "memory");
+  }
+  SRBD_DEV void tm_ld_finish(unsigned q[24], double v[12]) const {
+    // the registers are operands of the wait so that the compiler orders every use after it
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]),
+                   "+r"(q[8]), "+r"(q[9]), "+r"(q[10]), "+r"(q[11]), "+r"(q[12]), "+r"(q[13]), "+r"(q[14]), "+r"(q[15]),
+                   "+r"(q[16]), "+r"(q[17]), "+r"(q[18]), "+r"(q[19]), "+r"(q[20]), "+r"(q[21]), "+r"(q[22]), "+r"(q[23]) :: "memory");
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v[i] = __hiloint2double((int)q[2 * i + 1], (int)q[2 * i]);
+  }
+  SRBD_DEV void tm_ld(int slot, double v[12]) const {
+    unsigned q[24];
+    tm_ld_issue(slot, q);
+    tm_ld_finish(q, v);
+  }
+#else
+  double* tme;                  // host emulation: 32 lanes x 5 slots x 12 doubles of lane-private memory
+  SRBD_DEV void tm_st(int slot, const double v[12]) const { for (int i = 0; i < 12; ++i) tme[60 * lane + 12 * slot + i] = v[i]; }
+  SRBD_DEV void tm_ld(int slot, double v[12]) const { for (int i = 0; i < 12; ++i) v[i] = tme[60 * lane + 12 * slot + i]; }
+  SRBD_DEV void tm_ld_issue(int slot, unsigned q[24]) const { q[0] = (unsigned)slot; }
+  SRBD_DEV void tm_ld_finish(unsigned q[24], double v[12]) const { tm_ld((int)q[0], v); }
+#endif
+  // -(row rr of the block whose load was issued into q) . v
+  SRBD_DEV double trow_dot(unsigned q[24], const double v[12]) const {
+    double nr[12];
+    tm_ld_finish(q, nr);
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+#pragma unroll
+    for (int m = 0; m < 12; m += 3) { q0 = fma(-nr[m], v[m], q0); q1 = fma(-nr[m + 1], v[m + 1], q1); q2 = fma(-nr[m + 2], v[m + 2], q2); }
+    return q0 + q1 + q2;
+  }
 
   SRBD_DEV const double* gin(int i, int nnz) const { return pa->in[i] + e * nnz; }
   SRBD_DEV double* gout(int i, int nnz) const { return pa->out[i] + e * nnz; }
@@ -557,8 +628,8 @@ struct PdipmFastT {
     // rounds 0..3: top k = t (coupling from k-1) | bottom k = 9-t (coupling from k+1)
     // round 4: top k = 4 | bottom: S_55 - C_6' P_6 C_6 (block 5 with its coupling from 6), parked packed in P(5)
     // round 5: top k = 5: the parked rows, coupling from 4, sweep ; bottom idle
-    // The own row of the neighbour's inverse is re-read from the packed storage, the three other
-    // rows a lane needs come from the 72-entry hand-over window.
+    // The own row of the neighbour's inverse is re-read from tensor memory (fp32 mode: from the packed storage), the
+    // three other rows a lane needs come from the 72-entry hand-over window.
     double* vy = sm + SM::OFF_VY;
 #pragma unroll 1
     for (int t = 0; t < 6; ++t) {
@@ -573,9 +644,13 @@ struct PdipmFastT {
       }
       if (t > 0) {
         R o[12];
-        const R* Pn = P((t == 5) ? 4 : (h ? k + 1 : k - 1));
+        if constexpr (kTm) {
+          tm_ld(t - 1, o);    // own row of the block this half eliminated in the previous round (round 5: block 4)
+        } else {
+          const R* Pn = P((t == 5) ? 4 : (h ? k + 1 : k - 1));
 #pragma unroll
-        for (int c = 0; c < 12; ++c) o[c] = pe(Pn, c);
+          for (int c = 0; c < 12; ++c) o[c] = pe(Pn, c);
+        }
         couple(n, o, pr(h), h);
       }
       if (t == 4 && h == 1) {
@@ -604,10 +679,16 @@ struct PdipmFastT {
         const int kn = (t < 3) ? (h ? k - 1 : k + 1) : (t == 3 ? (h ? 5 : 4) : 5);
         if (act && r < 12) vy[12 * kn + rr] -= d;
       }
+      if constexpr (kTm) {
+        // warp-collective: every lane stores (the idle bottom half of round 4 writes a row nobody reads)
+        if (t < 5) tm_st(t, n);
+      }
       if (act) {
-        R* Pk = P(k);
+        if (!kTm || t == 5) {     // fp64: only the merge block is kept packed in shared memory
+          R* Pk = P(k);
 #pragma unroll
-        for (int c = 0; c < 12; ++c) if (c <= rr) pe(Pk, c) = n[c];
+          for (int c = 0; c < 12; ++c) if (c <= rr) pe(Pk, c) = n[c];
+        }
         const int slot = h ? rr : rr - 6;
         if (slot >= 0 && slot < 6) st12(pr(h) + 12 * slot, n);
       }
@@ -645,9 +726,12 @@ struct PdipmFastT {
 #pragma unroll 1
       for (int t = 1; t < 6; ++t) {
         const bool act = (t < 5) || (h == 0);
+        unsigned tq[24];
+        if constexpr (kTm) tm_ld_issue(t - 1, tq);
         double tv[12];
         ld12(vnb, tv);
-        b[rr] = prow_dot(Pnb, tv);
+        if constexpr (kTm) b[rr] = trow_dot(tq, tv);
+        else b[rr] = prow_dot(Pnb, tv);
         w.sync();
         const double d = cv0 * b[rr] + cv1 * b[j1] + cv2 * b[j2] + cv3 * b[j3];
         vnb += 12 * dk; Pnb += 78 * dk;
@@ -673,14 +757,21 @@ struct PdipmFastT {
 #pragma unroll 1
       for (int t = 1; t < 6; ++t) {
         const double* yn = vk;                  // the block solved in the previous trip
-        const bool act = (t < 5) || (h == 0);   // the bottom half has no sixth block
+        // the bottom half has four blocks for the top half's five.  Packed storage: it idles in the last trip.  Tensor
+        // memory: it idles in the FIRST trip (6 7 8 9 in trips 2..5 next to 3 2 1 0), so that both halves read the slot
+        // 5 - t -- the rows were stored in elimination order, top block t and bottom block 9 - t in slot t
+        const bool act = kTm ? ((t >= 2) || (h == 0)) : ((t < 5) || (h == 0));
+        unsigned tq[24];
+        if constexpr (kTm) tm_ld_issue(5 - t, tq);
         if (act) { vk -= 12 * dk; Pk -= 78 * dk; }
         const double tk = vk[rr] - (cv0 * yn[rr] + cv1 * yn[j1] + cv2 * yn[j2] + cv3 * yn[j3]);
         b[rr] = tk;
         w.sync();
         double bv[12];
         ld12(b, bv);
-        const double dy = prow_dot(Pk, bv);
+        double dy;
+        if constexpr (kTm) dy = trow_dot(tq, bv);
+        else dy = prow_dot(Pk, bv);
         if (act && r < 12) vk[rr] = dy;
         w.sync();
       }

@@ -41,11 +41,13 @@ static int g_f32_factor = 0;   // PdipmArgs::precision: 1 / 2 = the reduced-prec
 template <bool kF32>
 static void run_env_fast_t(const PdipmArgs& A, long long e, const StageSlot* slots) {
   std::vector<double> smem(FastSmem::SIZE, 0.0);
+  std::vector<double> tmem(32 * 60, 0.0);     // stands in for the warp's tensor-memory slots (lane-private rows)
   run_warp([&](int lane) {
     PdipmFastT<kF32> W;
     W.w.lane_ = lane;
     W.sm = smem.data();
     W.slots = slots;
+    W.tme = tmem.data();
     W.run(A, e);
   });
 }
