@@ -48,6 +48,11 @@ enum : int {
 
 struct FastSmem {
   static constexpr int OFF_P = 0;          // 10 x 78 packed lower; scratch for iterates in phase A
+  // fp64 path (the blocks' rows are in tensor memory; phase A's scratch ends at 500, the fused set-up's at 345): the two
+  // symmetric blocks that are still exchanged through shared memory are kept as FULL rows [12][12] -- row loads / stores
+  // with immediate offsets, no packed-offset registers at all
+  static constexpr int OFF_P5F = 356;      // merge block 5: parked S_55 - C_6' P_6 C_6 (round 4 -> 5), then N_5
+  static constexpr int OFF_SXF = 500;      // state part of S_kk including its diagonal term
   static constexpr int OFF_VX = 780;       // 240  r1~ -> dx
   static constexpr int OFF_VY = 1020;      // 140  re -> rho -> t -> dy
   static constexpr int OFF_PSI = 1160;     // 10 x 14
@@ -126,7 +131,8 @@ struct PdipmFastT {
   const PdipmArgs* pa;
   long long e;
   int lane, h, r, rr;
-  int prow[12];                 // packed offsets of row rr, in BYTES of the block's precision (one add per access)
+  int prow[kF32 ? 12 : 1];      // packed offsets of row rr, in BYTES of the block's precision (one add per access);
+                                //   fp32 mode only -- the fp64 path has no packed block left
   int bs0, bs1;                 // sparse rows of column rr of Bbar
   double c0[4], c1[4];          // row rr of C = Abar diag(phix)  /  row rr of C'
   int i0[3], i1[3];             // their off-diagonal column indices
@@ -277,8 +283,10 @@ struct PdipmFastT {
     // ---- per-lane registers ----------------------------------------------------------
     // (the lane's own row start is looked up once: kRow[] with a run-time index is a chain of selects)
     const int myrow = pkf_row(rr);
+    if constexpr (kF32) {
 #pragma unroll
-    for (int m = 0; m < 12; ++m) prow[m] = (m <= rr ? myrow + m : pkf_row(m) + rr) * (int)sizeof(R);
+      for (int m = 0; m < 12; ++m) prow[m] = (m <= rr ? myrow + m : pkf_row(m) + rr) * (int)sizeof(R);
+    }
     bs0 = 3 + rr % 3; bs1 = 9 + rr % 3;
     phx_rr = f[FB_PHX + rr];
     {
@@ -317,7 +325,14 @@ struct PdipmFastT {
         double acc = c0[0] * PdipmWarp<true>::abar(A, j, q);
 #pragma unroll
         for (int a = 0; a < 3; ++a) acc += c0[1 + a] * PdipmWarp<true>::abar(A, j, i0[a]);
-        f[FB_SX + myrow + j] = acc;     // pkf(q, j) for j <= q: the lane's own row is contiguous
+        if constexpr (kTm) {            // the same value at both mirror positions: exactly symmetric, as the packed form is
+          double* sxf = sm + SM::OFF_SXF;
+          const double v = (j == q) ? acc + (phx_rr + IP_DELTA) : acc;
+          sxf[12 * q + j] = v;
+          sxf[12 * j + q] = v;
+        } else {
+          f[FB_SX + myrow + j] = acc;   // pkf(q, j) for j <= q: the lane's own row is contiguous
+        }
       }
     }
     {   // inequality row r
@@ -516,8 +531,16 @@ struct PdipmFastT {
     // state part: delta + phix on the diagonal, A phix A' (absent for k = 0: x_0 is a parameter)
     const R fk = (k == 0) ? (R)0 : (R)1;
     const R dg = (R)(phx_rr + IP_DELTA);
+    if constexpr (kTm) {
+      ld12(sm + SM::OFF_SXF + 12 * rr, a);
+      if (k == 0) {      // x_0 is a parameter: only the diagonal term (round 0 of the top half; no other round enters)
 #pragma unroll
-    for (int j = 0; j < 12; ++j) a[j] = fmaR(fk, (R)*reinterpret_cast<const double*>(reinterpret_cast<const char*>(f + FB_SX) + (kF32 ? 2 : 1) * prow[j]), (rr == j) ? dg : (R)0);
+        for (int j = 0; j < 12; ++j) a[j] = (rr == j) ? dg : (R)0;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) a[j] = fmaR(fk, (R)*reinterpret_cast<const double*>(reinterpret_cast<const char*>(f + FB_SX) + 2 * prow[j]), (rr == j) ? dg : (R)0);
+    }
     w.sync();
     {
       R pl[12];
@@ -638,9 +661,12 @@ struct PdipmFastT {
       R n[12];
       if (t < 5) form_row(k, n);
       else {
-        const R* P5 = P(5);
+        if constexpr (kTm) ld12(sm + SM::OFF_P5F + 12 * rr, n);
+        else {
+          const R* P5 = P(5);
 #pragma unroll
-        for (int c = 0; c < 12; ++c) n[c] = pe(P5, c);
+          for (int c = 0; c < 12; ++c) n[c] = pe(P5, c);
+        }
       }
       if (t > 0) {
         R o[12];
@@ -654,9 +680,12 @@ struct PdipmFastT {
         couple(n, o, pr(h), h);
       }
       if (t == 4 && h == 1) {
-        R* P5 = P(5);
+        if constexpr (kTm) { if (r < 12) st12(sm + SM::OFF_P5F + 12 * rr, n); }
+        else {
+          R* P5 = P(5);
 #pragma unroll
-        for (int c = 0; c < 12; ++c) if (c <= rr) pe(P5, c) = n[c];
+          for (int c = 0; c < 12; ++c) if (c <= rr) pe(P5, c) = n[c];
+        }
       }
       sweep_invert(n);
       if (fwd && t < 5) {
@@ -684,7 +713,9 @@ struct PdipmFastT {
         if (t < 5) tm_st(t, n);
       }
       if (act) {
-        if (!kTm || t == 5) {     // fp64: only the merge block is kept packed in shared memory
+        if constexpr (kTm) {      // fp64: only the merge block goes through shared memory (full rows)
+          if (t == 5 && r < 12) st12(sm + SM::OFF_P5F + 12 * rr, n);
+        } else {
           R* Pk = P(k);
 #pragma unroll
           for (int c = 0; c < 12; ++c) if (c <= rr) pe(Pk, c) = n[c];
@@ -750,7 +781,15 @@ struct PdipmFastT {
         w.sync();
         double bv[12];
         ld12(b, bv);
-        const double dy = prow_dot(Pk, bv);
+        double dy;
+        if constexpr (kTm) {
+          double nr[12];
+          ld12(sm + SM::OFF_P5F + 12 * rr, nr);
+          double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+#pragma unroll
+          for (int m = 0; m < 12; m += 3) { q0 = fma(-nr[m], bv[m], q0); q1 = fma(-nr[m + 1], bv[m + 1], q1); q2 = fma(-nr[m + 2], bv[m + 2], q2); }
+          dy = q0 + q1 + q2;
+        } else dy = prow_dot(Pk, bv);
         if (h == 0 && r < 12) vk[rr] = dy;
         w.sync();
       }
