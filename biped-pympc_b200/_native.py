@@ -22,7 +22,7 @@ QP_NNZ_OUT = (240, 240, 1196, 140, 280, 160)
 IP_NNZ_IN = (240, 280, 1196, 240, 160, 140, 240, 160, 160, 140)
 IP_NNZ_OUT = (240, 160, 160, 140, 4, 1)
 WORK_DOUBLES = 6224          # general kernel, per env (srbd_args.h PDIPM_WORK_DOUBLES)
-WORK_DOUBLES_FAST = 1888     # fast kernel (STAGE_INVARIANT), per env (the fp64 path touches the first 1 504)
+WORK_DOUBLES_FAST = 2048     # fast kernel (STAGE_INVARIANT), per env (the fp64 path touches the first 1 664)
 
 _lib = None
 _P = ctypes.POINTER(ctypes.c_double)

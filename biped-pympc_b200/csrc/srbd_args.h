@@ -41,7 +41,7 @@ struct PdipmArgs {
 };
 constexpr int PDIPM_WORK_DOUBLES = 6224;  // general kernel, per env: directions + per-row barrier data (1 344) and the ten
                                           // stage buffers prepared once per call (10 x 488)
-constexpr int PDIPM_WORK_DOUBLES_FAST = 1888;   // fast kernel (SRBD_STAGE_INVARIANT, fused tick): srbd_pdipm_fast.h FW_END; the
-                                                // fp64 path touches the first 1 504
+constexpr int PDIPM_WORK_DOUBLES_FAST = 2048;   // fast kernel (SRBD_STAGE_INVARIANT, fused tick): srbd_pdipm_fast.h FW_END; the
+                                                // fp64 path touches the first 1 664
 
 }  // namespace srbd

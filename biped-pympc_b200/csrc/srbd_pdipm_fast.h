@@ -46,25 +46,30 @@ enum : int {
   FB_NSLOT = FB_RAW + 14
 };
 
-struct FastSmem {
+// kTm: the fp64 path, whose pivot-block rows live in tensor memory -- only the first 644 doubles of the P region are
+// needed (phase A's scratch [0, 500) with the merge block's full rows inside, the full rows of the state part of S_kk)
+// and the packed state part at the end of the stage data is not: 1 694 doubles per env, 16 envs per SM.  The fp32 mode
+// keeps the ten packed blocks: 1 908 doubles, 14 envs per SM.
+template <bool kTm>
+struct FastSmemT {
   static constexpr int OFF_P = 0;          // 10 x 78 packed lower; scratch for iterates in phase A
   // fp64 path (the blocks' rows are in tensor memory; phase A's scratch ends at 500, the fused set-up's at 345): the two
   // symmetric blocks that are still exchanged through shared memory are kept as FULL rows [12][12] -- row loads / stores
   // with immediate offsets, no packed-offset registers at all
   static constexpr int OFF_P5F = 356;      // merge block 5: parked S_55 - C_6' P_6 C_6 (round 4 -> 5), then N_5
   static constexpr int OFF_SXF = 500;      // state part of S_kk including its diagonal term
-  static constexpr int OFF_VX = 780;       // 240  r1~ -> dx
-  static constexpr int OFF_VY = 1020;      // 140  re -> rho -> t -> dy
-  static constexpr int OFF_PSI = 1160;     // 10 x 14
-  static constexpr int OFF_BC = 1300;      // 2 x 24 broadcast scratch per half
-  static constexpr int OFF_TR = 1348;      // 2 x 32: D*g and z of the stage being processed ...
-  static constexpr int OFF_PR = 1348;      // ... or (factor only) 2 x 72 handed-over rows of P
-  static constexpr int OFF_D = 1492;       // 160
-  static constexpr int OFF_FB = 1652;
-  static constexpr int OFF_TM = OFF_FB + FB_SIZE;   // 32-bit tensor-memory address of the warp's slot 0 (re-read at every
-                                                    // use: a register held across the whole solve costs spills)
-  static constexpr int SIZE = OFF_TM + 2;           // 2068 (even: every warp's region stays 16-byte aligned)
+  static constexpr int OFF_VX = kTm ? 644 : 780;   // 240  r1~ -> dx
+  static constexpr int OFF_VY = OFF_VX + 240;      // 140  re -> rho -> t -> dy
+  static constexpr int OFF_PSI = OFF_VY + 140;     // 10 x 14
+  static constexpr int OFF_BC = OFF_PSI + 140;     // 2 x 24 broadcast scratch per half
+  static constexpr int OFF_TR = OFF_BC + 48;       // 2 x 32: D*g and z of the stage being processed ...
+  static constexpr int OFF_PR = OFF_TR;            // ... or (factor only) 2 x 72 handed-over rows of P
+  static constexpr int OFF_FB = OFF_PR + 144;
+  static constexpr int OFF_TM = OFF_FB + (kTm ? FB_SX : FB_SIZE);   // 32-bit tensor-memory address of the warp's slot 0
+                                                    // (re-read at every use: a register held across the solve costs spills)
+  static constexpr int SIZE = OFF_TM + 2;           // even: every warp's region stays 16-byte aligned
 };
+static_assert(FastSmemT<true>::SIZE % 2 == 0 && FastSmemT<false>::SIZE % 2 == 0, "16-byte alignment of the warps' regions");
 // lane-private per-row scratch in the work buffer
 enum : int { FW_DX = 0, FW_DY = 240, FW_S = 380, FW_Z = 540, FW_Q = 700,
              // fused tick only: f of the states, c_d | c_d + A_d x0, F_max * contact
@@ -72,8 +77,9 @@ enum : int { FW_DX = 0, FW_DY = 240, FW_S = 380, FW_Z = 540, FW_Q = 700,
              // working copies of s, z and the bound h of the lane's rows: with ds, dz and D/W above they are addressed
              // as one per-row pointer + immediate (the caller's s / z buffers are read once and written once per call)
              FW_SV = 1024, FW_ZV = 1184, FW_H = 1344,
+             FW_D = 1504,    // D = W / (1 + delta W) of the row (written in phase A, read when the step is recovered)
              // fp32 pivot blocks with refinement only: re of the iteration (r4 of the affine solve), the unrefined dx
-             FW_RE = 1504, FW_RX = 1632, FW_END = 1872 };
+             FW_RE = 1664, FW_RX = 1792, FW_END = 2032 };
 static_assert(FW_END <= PDIPM_WORK_DOUBLES_FAST, "work buffer too small");
 
 // Packed storage of the symmetric 12x12 blocks (P_k, A phix A'): row i keeps its entries (i, 0..i) contiguous, as in the
@@ -119,7 +125,7 @@ SRBD_DEV float wrench_entry(const double* u0, const float* R, int idx) {
 // refinement against the fp64 Schur operator.  Accuracy and speed are measured, not promised: DESIGN.md section 8.
 template <bool kF32>
 struct PdipmFastT {
-  using SM = FastSmem;
+  using SM = FastSmemT<!kF32>;
   using R = typename std::conditional<kF32, float, double>::type;   // precision of the pivot blocks
   Warp w;
   double* sm;
@@ -1072,7 +1078,6 @@ struct PdipmFastT {
     const double* f = fb();
     double* vx = sm + SM::OFF_VX;
     double* vy = sm + SM::OFF_VY;
-    double* Dsm = sm + SM::OFF_D;
     double* sx = sm + SM::OFF_P;         // iterate scratch (phase A only): x | y | (hx + beta) x
     double* sy = sx + 240; double* xs = sx + 380;
     double* ws = gws();
@@ -1127,7 +1132,7 @@ struct PdipmFastT {
         const double D = W * q;
         const double Dg = fma(D, rs, -(q * zv));         // D (r2 / W - r3), r2 = -z, r3 = -rs
         row[FW_S] = fma(IP_DELTA, Dg, -rs); row[FW_Z] = Dg; row[FW_Q] = q;
-        Dsm[j] = D;
+        row[FW_D] = D;
         gdg = gather_rows(Dg, ga, gb); gz = gather_rows(zv, ga, gb);
         a_sz = fma(sv, zv, a_sz); a_rs = fma(rs, rs, a_rs);
         // Psi: pairs (0,1)->fx (2,3)->fy (4,5)->my ; (6,7) -> fz only
@@ -1262,7 +1267,7 @@ struct PdipmFastT {
     double* vy = sm + SM::OFF_VY;
     const int j = 16 * k + r;
     double* row = gws() + j;
-    const double sv = row[FW_SV], zv = row[FW_ZV], sS = row[FW_S], sZ = row[FW_Z];
+    const double sv = row[FW_SV], zv = row[FW_ZV], sS = row[FW_S], sZ = row[FW_Z], Dj = row[FW_D];
     double* b = bc();
     double* vu = vx + 120 + 12 * k;
     const double* dyk = vy + 12 * k;
@@ -1286,7 +1291,7 @@ struct PdipmFastT {
     w.sync();
     {
       const double gdu = f[goa] * vu[ca] + f[gob] * vu[cz];
-      const double Dg = sm[SM::OFF_D + j] * gdu;
+      const double Dg = Dj * gdu;
       const double dz = sZ + Dg;
       const double ds = fma(IP_DELTA, Dg, sS - gdu);
       row[FW_S] = ds; row[FW_Z] = dz;       // affine (pass 0) / combined (pass 1)

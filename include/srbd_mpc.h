@@ -109,7 +109,7 @@ int srbd_pattern(char which /* 'H','A','G' */, const int** colptr, const int** r
 int srbd_qp_form(const double* const* in17, double* const* out6, int B, void* stream);
 
 /* scratch doubles the caller must provide to srbd_pdipm for B environments when it is called with
- * `flags`: 1 888 per env with SRBD_STAGE_INVARIANT (the fast kernel), 6 224 per env without (the general
+ * `flags`: 2 048 per env with SRBD_STAGE_INVARIANT (the fast kernel), 6 224 per env without (the general
  * kernel parks its ten prepared stage buffers there). */
 size_t srbd_pdipm_work_doubles(int B, unsigned flags);
 

@@ -40,7 +40,7 @@ static void run_env(const PdipmArgs& A, long long e, const StageSlot* slots, int
 static int g_f32_factor = 0;   // PdipmArgs::precision: 1 / 2 = the reduced-precision pivot-block mode (PdipmFastT<true>)
 template <bool kF32>
 static void run_env_fast_t(const PdipmArgs& A, long long e, const StageSlot* slots) {
-  std::vector<double> smem(FastSmem::SIZE, 0.0);
+  std::vector<double> smem(FastSmemT<!kF32>::SIZE, 0.0);
   std::vector<double> tmem(32 * 60, 0.0);     // stands in for the warp's tensor-memory slots (lane-private rows)
   run_warp([&](int lane) {
     PdipmFastT<kF32> W;

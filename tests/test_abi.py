@@ -44,7 +44,7 @@ def test_nnz_tables():
     assert [lib.srbd_pdipm_nnz_out(i) for i in range(6)] == list(so.PDIPM_NNZ_OUT)
     assert lib.srbd_qp_former_nnz_in(17) < 0 and lib.srbd_pdipm_nnz_out(-1) < 0
     assert lib.srbd_pdipm_work_doubles(3, 0) == 3 * bp._native.WORK_DOUBLES
-    assert lib.srbd_pdipm_work_doubles(3, bp._native.STAGE_INVARIANT) == 3 * bp._native.WORK_DOUBLES_FAST == 3 * 1888
+    assert lib.srbd_pdipm_work_doubles(3, bp._native.STAGE_INVARIANT) == 3 * bp._native.WORK_DOUBLES_FAST == 3 * 2048
 
 
 def test_patterns_match_oracle_structure():
