@@ -685,7 +685,7 @@ def run_b200(args):
                    "envs_per_gpu": B, "iters": args.calls * args.iters, "horizon": 10, "parallelism": f"env-sharded x{world}, no collective",
                    "l2": "256 MB buffer written between timed iterations (L2 flush)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": n_e2e, "api": "Context.bind_host(...)() = srbd_mpc_solve_host on buffers validated once (pinned host buffers read and written over PCIe by the kernels themselves: the first 2058-env chunk in place, the second pulled into device staging by a co-resident prefetch kernel while the first solves)"},
+                "steps": n_e2e, "api": "Context.bind_host(...)() = srbd_mpc_solve_host on buffers validated once (pinned host buffers read and written over PCIe by the kernels themselves: the first 2368-env chunk -- one full round of the persistent kernel -- in place, the rest pulled into device staging by the copy engine while the first solves)"},
         "gpu_launches": args.steps,          # ONE kernel per step: fused assembly + PDIPM + wrench (pdipm_fast_kernel)
         "clocks": clocks,
     }

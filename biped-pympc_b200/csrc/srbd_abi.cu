@@ -530,25 +530,38 @@ int srbd_mpc_solve_host(srbd_ctx* c, const double* const* in17_host, const float
   // The batch is cut into chunks of whole CTAs' worth of envs that alternate between two streams:
   // the input traffic of one chunk (prefetch kernel below) overlaps the solve of the previous one.
   const int per_cta = pdipm_warps_per_cta(true);
-  int chunk = (zero_copy ? 147 : 74) * per_cta;     // 2 058 / 1 036 envs
+  int chunk = (zero_copy ? 148 : 74) * per_cta;     // 2 368 / 1 184 envs: one full round of the persistent kernel (16 warps on
+                                                    // every SM); the rest of a 4 096-env batch is its 11-12-warp round
   if (const char* ev = std::getenv("SRBD_HOST_CHUNK")) chunk = std::atoi(ev) > 0 ? std::atoi(ev) : chunk;   // tuning knob
   if (B <= chunk) chunk = B;
+  // The first chunk's staging is the only exposed transfer: when the batch needs more than one round anyway, the first
+  // chunk is the SMALLER round (3 of 4 envs per scheduler: 1 776 of a 4 096-env batch) and the full round follows
+  int chunk0 = chunk;
+  if (zero_copy && B > chunk && B - (chunk / 4) * 3 <= chunk) chunk0 = (chunk / 4) * 3;
+  if (const char* ev = std::getenv("SRBD_HOST_CHUNK0")) chunk0 = std::atoi(ev) > 0 ? std::atoi(ev) : chunk0;
+  if (chunk0 > B) chunk0 = B;
   // Any failure inside the loop leaves the loop (never returns from it): earlier chunks may still be in flight on the
   // two internal streams, reading and writing the caller's host buffers, so both streams are drained before returning.
 #define HOST_TRY(expr) { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { rc = cuda_fail(e__); break; } }
   int rc = SRBD_OK, ci = 0;
-  for (int e0 = 0; e0 < B; e0 += chunk, ++ci) {
-    const int nb = (B - e0 < chunk) ? B - e0 : chunk;
+  for (int e0 = 0; e0 < B; e0 += (ci == 0 ? chunk0 : chunk), ++ci) {
+    const int want = (ci == 0) ? chunk0 : chunk;
+    const int nb = (B - e0 < want) ? B - e0 : want;
     cudaStream_t st = (ci & 1) ? c->stream2 : c->stream;
     const size_t o = (size_t)e0;
     const double* din[QP_N_IN];
     const float* drot;
     float* dw;
-    // Chunks after the first are pulled into device staging by a co-resident prefetch kernel while the previous chunk
-    // solves, instead of being read in place by their own solve kernel (whose CTAs only become resident when the previous
-    // chunk's have finished): 0.89 -> 0.82 ms for 4 096 envs.  SRBD_HOST_PREFETCH=0 turns it off.
+    // Chunks after the first are pulled into device staging while the previous chunk solves, instead of being read in
+    // place by their own solve kernel (whose CTAs only become resident when the previous chunk's have finished):
+    // 0.89 -> 0.82 ms for 4 096 envs in round 1.  SRBD_HOST_PREFETCH=0 turns it off.
     static const bool prefetch = [] { const char* ev = std::getenv("SRBD_HOST_PREFETCH"); return !ev || std::atoi(ev) > 0; }();
-    if (zero_copy && prefetch && ci > 0) {
+    // The first chunk is staged too -- by the prefetch kernel, whose coalesced reads use the PCIe link far better than
+    // the solve warps' small in-place reads (0.695 -> 0.660 ms) -- and the second chunk's copies are ordered after it
+    // (one link).  SRBD_HOST_STAGE_FIRST=0: the first chunk is read in place by its solve kernel.
+    static const bool stage_first = [] { const char* ev = std::getenv("SRBD_HOST_STAGE_FIRST"); return !ev || std::atoi(ev) > 0; }();
+    if (zero_copy && prefetch && (ci > 0 || stage_first)) {
+      if (stage_first && ci == 1) HOST_TRY(cudaStreamWaitEvent(st, c->done2, 0));
       const double* src[QP_N_IN]; double* dst[QP_N_IN]; int n[QP_N_IN];
       for (int i = 0; i < QP_N_IN; ++i) {
         src[i] = zin[i] ? zin[i] + o * kQpNnzIn[i] : nullptr;
@@ -556,7 +569,19 @@ int srbd_mpc_solve_host(srbd_ctx* c, const double* const* in17_host, const float
         n[i] = nb * kQpNnzIn[i];
         din[i] = dst[i];
       }
-      HOST_TRY(launch_prefetch(src, dst, n, zrot + o * 9, c->rot_stage + o * 9, nb * 9, num_sms(), st));
+      // The copy engine moves the staged chunk (14 copies): the persistent fp64 solve kernel holds every register of its
+      // SM (16 warps x 128), so the prefetch KERNEL of round 1 -- which co-resided with the 14-warp solve -- would only
+      // start when the previous chunk's CTAs have left.  SRBD_HOST_COPYENGINE=0 selects the kernel (0.708 vs 0.696 ms).
+      static const bool copy_engine = [] { const char* ev = std::getenv("SRBD_HOST_COPYENGINE"); return !ev || std::atoi(ev) > 0; }();
+      if (copy_engine && ci > 0) {
+        for (int i = 0; i < QP_N_IN; ++i)
+          if (src[i]) HOST_TRY(cudaMemcpyAsync(dst[i], in17_host[i] + o * kQpNnzIn[i], (size_t)n[i] * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (rc) break;
+        HOST_TRY(cudaMemcpyAsync(c->rot_stage + o * 9, rotation_body_host + o * 9, (size_t)nb * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+      } else {
+        HOST_TRY(launch_prefetch(src, dst, n, zrot + o * 9, c->rot_stage + o * 9, nb * 9, num_sms(), st));
+      }
+      if (stage_first && ci == 0) HOST_TRY(cudaEventRecord(c->done2, st));
       drot = c->rot_stage + o * 9;
       dw = zw + o * 12;
     } else if (zero_copy) {
