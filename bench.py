@@ -626,6 +626,28 @@ def run_b200(args):
         total_ms = float(t.item())
     value = world * B * args.steps / (total_ms * 1e-3)
 
+    # ---- p50 / p99 step latency (the metric's second half; SURVEY 8d: 1 000 repetitions after 50 warm-ups, CUDA events
+    #      around the stream work of one batched call, L2 flushed between repetitions) -------------------------------
+    for _ in range(50):
+        step()
+    lat_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.latency_reps)]
+    torch.cuda.synchronize()
+    t_lat0 = time.time()
+    for a, b in lat_ev:
+        flush.fill_(1.0)
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    t_lat1 = time.time()
+    lat_ms = sorted(a.elapsed_time(b) for a, b in lat_ev)
+    # clocks and throttle reasons: sampled over the K timed steps AND the latency loop (the K steps alone are shorter than
+    # one 20 ms sampling period at the default K)
+    clocks = sampler.stop(t_wall0, t_lat1)
+    clocks["window"] = "timed steps + latency loop" if clocks.get("window") == "timed region" else clocks.get("window")
+
+    # (the e2e leg runs AFTER the clock sampler has been stopped: `nvidia-smi -lms 20` polls the driver every 20 ms and
+    #  contends with the ~20 CUDA API calls of a host-entry tick -- 0.71 ms in a quiet process, 0.77 ms next to the poller)
     # ---- e2e: host buffers through the C-ABI (H2D + kernels + D2H inside the timed region) ----
     # x, u (inputs 1, 2) are the linearisation point, all ones at the reference call site
     # (mpc_controller_cusadi.py:55-56) and dead for this LTV-linear problem: the host API takes
@@ -652,26 +674,6 @@ def run_b200(args):
     e2e_value = world * B * n_e2e / e2e_s
     h2d = sum(a.numel() * 8 for a in h_in if a is not None) + h_rot.numel() * 4
     d2h = h_w.numel() * 4
-
-    # ---- p50 / p99 step latency (the metric's second half; SURVEY 8d: 1 000 repetitions after 50 warm-ups, CUDA events
-    #      around the stream work of one batched call, L2 flushed between repetitions) -------------------------------
-    for _ in range(50):
-        step()
-    lat_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.latency_reps)]
-    torch.cuda.synchronize()
-    t_lat0 = time.time()
-    for a, b in lat_ev:
-        flush.fill_(1.0)
-        a.record()
-        step()
-        b.record()
-    torch.cuda.synchronize()
-    t_lat1 = time.time()
-    lat_ms = sorted(a.elapsed_time(b) for a, b in lat_ev)
-    # clocks and throttle reasons: sampled over the K timed steps AND the latency loop (the K steps alone are shorter than
-    # one 20 ms sampling period at the default K)
-    clocks = sampler.stop(t_wall0, t_lat1)
-    clocks["window"] = "timed steps + latency loop" if clocks.get("window") == "timed region" else clocks.get("window")
 
     default_wl = (args.calls == 1 and args.iters == ITERS and args.tol <= 0)
     line = {

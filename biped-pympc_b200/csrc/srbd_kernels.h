@@ -13,7 +13,9 @@ cudaError_t qp_form_upload_table();
 cudaError_t launch_qp_form(const QpFormArgs& args, int B, int num_sms, cudaStream_t stream);
 
 cudaError_t pdipm_upload_tables();
-cudaError_t launch_pdipm(const PdipmArgs& args, int B, bool stage_invariant, int num_sms, cudaStream_t stream);
+// leave_room: fast fp64 path only -- launch the 12-warp instance (3 per scheduler) when the batch fits one round of it, so
+// that a small kernel (the host entry's prefetch) can co-reside: the 16-warp CTA holds every register of its SM
+cudaError_t launch_pdipm(const PdipmArgs& args, int B, bool stage_invariant, int num_sms, cudaStream_t stream, bool leave_room = false);
 int pdipm_warps_per_cta(bool stage_invariant);
 
 // u0 -> body-frame wrench (mpc_controller_cusadi.py:186-203)
