@@ -16,8 +16,8 @@
 //     of being re-gathered from the packed storage;
 //   * the per-inequality-row data (s, z, the two direction slots, D w^-1) is lane-private and
 //     lives in the L2-resident work buffer; only D stays in shared memory;
-//   * 2 068 doubles of shared memory per warp -> 14 warps (environments) per SM; the lanes' rows of the pivot-block
-//     inverses in tensor memory (fp64 path).
+//   * fp64 path: the lanes' rows of the pivot-block inverses in tensor memory, 1 694 doubles of shared memory per warp
+//     -> 16 warps (environments) per SM, persistent; fp32 mode: ten packed blocks in shared memory, 1 908 doubles, 14 warps.
 //
 // Compiled for the GPU (srbd_pdipm.cu) and, for tests only, for the host under the warp
 // emulator of srbd_warp.h.
@@ -130,7 +130,7 @@ struct PdipmFastT {
   Warp w;
   double* sm;
   const StageSlot* slots;
-  // Register diet: 14 warps per SM are allocated as 16, i.e. 128 registers per thread.  Only what
+  // Register diet: 13-16 warps per SM put four on one scheduler (16 K registers), i.e. 128 registers per thread.  Only what
   // the elimination rounds need every time stays in registers; everything else is re-read from
   // shared memory (short latency) instead of being spilled to local memory (L2 latency: the 28 KB
   // of L1 left beside 228 KB of shared memory cannot hold the spills of 448 threads).
