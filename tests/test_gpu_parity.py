@@ -605,10 +605,11 @@ def test_operator_accepts_a_casadi_like_function_and_checks_its_buffers(golden):
         bp.qp_form(bad)
 
 
-@pytest.mark.parametrize("B", [1, 13, 14, 15, 29, 2073])
+@pytest.mark.parametrize("B", [1, 13, 15, 16, 17, 147, 148, 149, 2073, 2367, 2368, 2369, 4145])
 def test_fused_tick_ragged_batches(B):
-    """CTA boundaries of the fused kernel (14 envs per CTA, 148 CTAs per wave): a batch gives the same
-    per-env answer whatever its size, and the same as assembly + solve + wrench as three launches."""
+    """Round boundaries of the persistent fused kernel (at most one CTA per SM, 16 warps; env = round * 16 G + warp * G +
+    cta with G = min(SMs, B) CTAs): a batch gives the same per-env answer whatever its size, and the same as assembly +
+    solve + wrench as three launches."""
     inp, rot = bp.workload.make_batch(B, seed=100 + B)
     ins = _dev(inp)
     rot_t = torch.as_tensor(rot, dtype=torch.float32, device=DEV)

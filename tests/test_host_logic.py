@@ -45,3 +45,24 @@ def test_mirror_classes_expose_the_reference_surface():
         assert hasattr(bp.GaitGeneratorB200, name), name
     for name in ("init_solver", "run", "reset", "build_state"):
         assert hasattr(bp.MPCControllerB200, name), name
+
+
+@pytest.mark.parametrize("B,sms", [(1, 148), (100, 148), (148, 148), (149, 148), (2368, 148), (2369, 148), (4096, 148), (65536, 148), (5000, 132)])
+def test_persistent_kernel_env_numbering_covers_every_env_once(B, sms):
+    """The fp64 fast kernel is persistent (csrc/srbd_pdipm.cu): G = min(SMs, B) CTAs of 16 warps, warp w of CTA s solves
+    envs e = w * G + s, then e += 16 G.  Every env exactly once; within a round the envs fill warps 0.. of ALL CTAs first,
+    so a partial round loads every SM (and every scheduler: warp w runs on scheduler w % 4) evenly."""
+    G, W = min(sms, B), 16
+    seen = []
+    per_cta_last_round = {}
+    for s_ in range(G):
+        for w in range(W):
+            e = w * G + s_
+            while e < B:
+                seen.append(e)
+                if e >= (B // (W * G)) * W * G:
+                    per_cta_last_round[s_] = per_cta_last_round.get(s_, 0) + 1
+                e += W * G
+    assert sorted(seen) == list(range(B))
+    if per_cta_last_round:
+        assert max(per_cta_last_round.values()) - min(per_cta_last_round.get(s_, 0) for s_ in range(G)) <= 1
