@@ -144,6 +144,9 @@ struct PdipmFastT {
   int i0[3], i1[3];             // their off-diagonal column indices
   double phx_rr;                // 1/(hx + beta) of state rr
   int goa, gob, ca, cz;         // inequality row r: G(r, ca) = fb[goa], G(r, cz) = fb[gob]
+  double gva, gvb;              // ... and the two coefficients themselves (constant over the call; 20 uses per iteration:
+                                //   two registers each beat re-reading them from shared memory since the packed-offset
+                                //   registers are gone, -1.2 %)
   int psk, psi_i, psf;          // role of input column rr in Psi: kind, index, foot
   int doff, moff;               // fb offsets of its constant Psi diagonal / 1/mx_den (or of a zero)
   int g_src;                    // lane that ends up with sum_j G[j, rr] v_j in gather_rows (-1: the column has no rows)
@@ -363,6 +366,8 @@ struct PdipmFastT {
       if (c < 6) g_src = (lane & 16) + 8 * (c / 3) + (c % 3 == 2 ? 6 : 2 * (c % 3));
       else if (c == 7 || c == 10) g_src = (lane & 16) + 8 * (c == 10) + 4;
     }
+    w.sync();
+    gva = f[goa]; gvb = f[gob];
     w.sync();
     return bad;
   }
@@ -915,7 +920,7 @@ struct PdipmFastT {
         // ---- s = max(h - G x, s_min); z kept (floored) where the row's bound is unchanged, re-centred (z = mu0 / s)
         //      where the schedule changed it (rows 7 / 15 of a stage: fz <= F_max * contact) -----------------------
         const double* f = fb();
-        const double ga = f[goa], gb = f[gob];
+        const double ga = gva, gb = gvb;
         const int q7 = (r & 7) == 7;
 #pragma unroll
         for (int t = 0; t < 5; ++t) {
@@ -929,7 +934,7 @@ struct PdipmFastT {
         }
       } else if (A.cold_start) {   // s = max(h - G x, 1) (x = 0 unless warm); in fused mode h only exists after the set-up
         const double* f = fb();
-        const double ga = f[goa], gb = f[gob];
+        const double ga = gva, gb = gvb;
 #pragma unroll
         for (int t = 0; t < 5; ++t) {
           const int k = h ? 9 - t : t, j = 16 * k + r;
@@ -1123,7 +1128,7 @@ struct PdipmFastT {
       double* ps = psi(k);
       double gdg, gz;
       {   // inequality row j
-        const double ga = f[goa], gb = f[gob];
+        const double ga = gva, gb = gvb;
         const double pga = w.shfl_xor(ga, 1), pgb = w.shfl_xor(gb, 1);
         const double rs = ga * u[ca] + gb * u[cz] + sv - hv;
         const double si = rcp(sv);
@@ -1204,7 +1209,7 @@ struct PdipmFastT {
     const double r2 = -(rcp(sv) * (sv * zv + dsa * dza - smu));
     const double Dg = q * r2;
     row[FW_S] = fma(IP_DELTA, Dg, dsa); row[FW_Z] = dza + Dg;
-    vx[120 + 12 * k + rr] = -gather_rows(Dg, fb()[goa], fb()[gob]);
+    vx[120 + 12 * k + rr] = -gather_rows(Dg, gva, gvb);
     w.sync();
   }
 
@@ -1290,7 +1295,7 @@ struct PdipmFastT {
     }
     w.sync();
     {
-      const double gdu = f[goa] * vu[ca] + f[gob] * vu[cz];
+      const double gdu = gva * vu[ca] + gvb * vu[cz];
       const double Dg = Dj * gdu;
       const double dz = sZ + Dg;
       const double ds = fma(IP_DELTA, Dg, sS - gdu);
