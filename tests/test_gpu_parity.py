@@ -469,12 +469,12 @@ def test_fused_tick_equals_two_step_path(batch64):
     ctx.close()
 
 
-@pytest.mark.parametrize("pinned", [True, False])
-def test_host_entry_chunks_and_default_linearisation_point(pinned):
-    """srbd_mpc_solve_host cuts the batch into chunks on two streams (pinned buffers are read /
-    written in place over PCIe, pageable ones are staged) and accepts NULL for the (dead)
-    linearisation point x, u = ones: all of it must leave the result bit-identical."""
-    B = 2500                                   # 2 (pinned) / 3 (pageable) chunks, the last one ragged
+@pytest.mark.parametrize("pinned,B", [(True, 2500), (False, 2500), (True, 9000)])
+def test_host_entry_chunks_and_default_linearisation_point(pinned, B):
+    """srbd_mpc_solve_host cuts the batch into chunks on two streams (pinned buffers: staged by the prefetch kernel /
+    the copy engine, the wrench written in place over PCIe; pageable ones staged with cudaMemcpyAsync) and accepts NULL
+    for the (dead) linearisation point x, u = ones: all of it must leave the result bit-identical.
+    2 500 envs: the smaller round first (1 776 + 724; pageable: 3 chunks); 9 000: four chunks alternating streams."""
     inp, rot = bp.workload.make_batch(B, seed=77)
     ctx = bp.Context(B)
     rot_t = torch.as_tensor(rot, dtype=torch.float32, device=DEV)
