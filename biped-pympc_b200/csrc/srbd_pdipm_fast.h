@@ -16,7 +16,7 @@
 //     of being re-gathered from the packed storage;
 //   * the per-inequality-row data (s, z, the two direction slots, D w^-1) is lane-private and
 //     lives in the L2-resident work buffer; only D stays in shared memory;
-//   * fp64 path: the lanes' rows of the pivot-block inverses in tensor memory, 1 694 doubles of shared memory per warp
+//   * fp64 path: the lanes' rows of the pivot-block inverses in tensor memory, 1 742 doubles of shared memory per warp
 //     -> 16 warps (environments) per SM, persistent; fp32 mode: ten packed blocks in shared memory, 1 908 doubles, 14 warps.
 //
 // Compiled for the GPU (srbd_pdipm.cu) and, for tests only, for the host under the warp
@@ -48,7 +48,7 @@ enum : int {
 
 // kTm: the fp64 path, whose pivot-block rows live in tensor memory -- only the first 644 doubles of the P region are
 // needed (phase A's scratch [0, 500) with the merge block's full rows inside, the full rows of the state part of S_kk)
-// and the packed state part at the end of the stage data is not: 1 694 doubles per env, 16 envs per SM.  The fp32 mode
+// and the packed state part at the end of the stage data is not: 1 742 doubles per env, 16 envs per SM.  The fp32 mode
 // keeps the ten packed blocks: 1 908 doubles, 14 envs per SM.
 template <bool kTm>
 struct FastSmemT {
@@ -56,15 +56,19 @@ struct FastSmemT {
   // fp64 path (the blocks' rows are in tensor memory; phase A's scratch ends at 500, the fused set-up's at 345): the two
   // symmetric blocks that are still exchanged through shared memory are kept as FULL rows [12][12] -- row loads / stores
   // with immediate offsets, no packed-offset registers at all
-  static constexpr int OFF_P5F = 356;      // merge block 5: parked S_55 - C_6' P_6 C_6 (round 4 -> 5), then N_5
-  static constexpr int OFF_SXF = 500;      // state part of S_kk including its diagonal term
-  static constexpr int OFF_VX = kTm ? 644 : 780;   // 240  r1~ -> dx
+  // (row stride FS = 14 doubles, like Bbar: the twelve lanes of a half-warp then read their rows with two wavefronts
+  //  per 16-byte load instead of three at stride 12 -- profiles/smem_bcast_r1_wavefronts.csv)
+  static constexpr int FS = 14;
+  static constexpr int OFF_P5F = 332;      // merge block 5: parked S_55 - C_6' P_6 C_6 (round 4 -> 5), then N_5  [12][FS]
+  static constexpr int OFF_SXF = 500;      // state part of S_kk including its diagonal term                     [12][FS]
+  static constexpr int OFF_VX = kTm ? 668 : 780;   // 240  r1~ -> dx
   static constexpr int OFF_VY = OFF_VX + 240;      // 140  re -> rho -> t -> dy
   static constexpr int OFF_PSI = OFF_VY + 140;     // 10 x 14
   static constexpr int OFF_BC = OFF_PSI + 140;     // 2 x 24 broadcast scratch per half
   static constexpr int OFF_TR = OFF_BC + 48;       // 2 x 32: D*g and z of the stage being processed ...
-  static constexpr int OFF_PR = OFF_TR;            // ... or (factor only) 2 x 72 handed-over rows of P
-  static constexpr int OFF_FB = OFF_PR + 144;
+  static constexpr int HS = kTm ? 14 : 12;         // row stride of the hand-over window (fp64: 14, as for the full rows)
+  static constexpr int OFF_PR = OFF_TR;            // ... or (factor only) 2 x 6 handed-over rows of P
+  static constexpr int OFF_FB = OFF_PR + 2 * 6 * HS;
   static constexpr int OFF_TM = OFF_FB + (kTm ? FB_SX : FB_SIZE);   // 32-bit tensor-memory address of the warp's slot 0
                                                     // (re-read at every use: a register held across the solve costs spills)
   static constexpr int SIZE = OFF_TM + 2;           // even: every warp's region stays 16-byte aligned
@@ -234,7 +238,7 @@ struct PdipmFastT {
   SRBD_DEV double* fb() const { return sm + SM::OFF_FB; }
   SRBD_DEV double* bc() const { return sm + SM::OFF_BC + 24 * h; }
   SRBD_DEV double* tr() const { return sm + SM::OFF_TR + 32 * h; }
-  SRBD_DEV R* pr(int hh) const { return reinterpret_cast<R*>(sm + SM::OFF_PR) + 72 * hh; }
+  SRBD_DEV R* pr(int hh) const { return reinterpret_cast<R*>(sm + SM::OFF_PR) + 6 * SM::HS * hh; }
   SRBD_DEV R* bcr() const { return reinterpret_cast<R*>(sm + SM::OFF_BC + 24 * h); }   // broadcast scratch in block precision
   SRBD_DEV double* psi(int k) const { return sm + SM::OFF_PSI + 14 * k; }
 
@@ -337,8 +341,8 @@ struct PdipmFastT {
         if constexpr (kTm) {            // the same value at both mirror positions: exactly symmetric, as the packed form is
           double* sxf = sm + SM::OFF_SXF;
           const double v = (j == q) ? acc + (phx_rr + IP_DELTA) : acc;
-          sxf[12 * q + j] = v;
-          sxf[12 * j + q] = v;
+          sxf[SM::FS * q + j] = v;
+          sxf[SM::FS * j + q] = v;
         } else {
           f[FB_SX + myrow + j] = acc;   // pkf(q, j) for j <= q: the lane's own row is contiguous
         }
@@ -543,7 +547,7 @@ struct PdipmFastT {
     const R fk = (k == 0) ? (R)0 : (R)1;
     const R dg = (R)(phx_rr + IP_DELTA);
     if constexpr (kTm) {
-      ld12(sm + SM::OFF_SXF + 12 * rr, a);
+      ld12(sm + SM::OFF_SXF + SM::FS * rr, a);
       if (k == 0) {      // x_0 is a parameter: only the diagonal term (round 0 of the top half; no other round enters)
 #pragma unroll
         for (int j = 0; j < 12; ++j) a[j] = (rr == j) ? dg : (R)0;
@@ -592,13 +596,13 @@ struct PdipmFastT {
     R U[12];
     {
       R t1[12];
-      ld12(hand + 12 * s1, t1);
+      ld12(hand + SM::HS * s1, t1);
 #pragma unroll
       for (int m = 0; m < 12; ++m) U[m] = fmaR(cv1, t1[m], cv0 * own[m]);
-      ld12(hand + 12 * s2, t1);
+      ld12(hand + SM::HS * s2, t1);
 #pragma unroll
       for (int m = 0; m < 12; ++m) U[m] = fmaR(cv2, t1[m], U[m]);
-      ld12(hand + 12 * s3, t1);
+      ld12(hand + SM::HS * s3, t1);
 #pragma unroll
       for (int m = 0; m < 12; ++m) U[m] = fmaR(cv3, t1[m], U[m]);
     }
@@ -672,7 +676,7 @@ struct PdipmFastT {
       R n[12];
       if (t < 5) form_row(k, n);
       else {
-        if constexpr (kTm) ld12(sm + SM::OFF_P5F + 12 * rr, n);
+        if constexpr (kTm) ld12(sm + SM::OFF_P5F + SM::FS * rr, n);
         else {
           const R* P5 = P(5);
 #pragma unroll
@@ -691,7 +695,7 @@ struct PdipmFastT {
         couple(n, o, pr(h), h);
       }
       if (t == 4 && h == 1) {
-        if constexpr (kTm) { if (r < 12) st12(sm + SM::OFF_P5F + 12 * rr, n); }
+        if constexpr (kTm) { if (r < 12) st12(sm + SM::OFF_P5F + SM::FS * rr, n); }
         else {
           R* P5 = P(5);
 #pragma unroll
@@ -725,14 +729,14 @@ struct PdipmFastT {
       }
       if (act) {
         if constexpr (kTm) {      // fp64: only the merge block goes through shared memory (full rows)
-          if (t == 5 && r < 12) st12(sm + SM::OFF_P5F + 12 * rr, n);
+          if (t == 5 && r < 12) st12(sm + SM::OFF_P5F + SM::FS * rr, n);
         } else {
           R* Pk = P(k);
 #pragma unroll
           for (int c = 0; c < 12; ++c) if (c <= rr) pe(Pk, c) = n[c];
         }
         const int slot = h ? rr : rr - 6;
-        if (slot >= 0 && slot < 6) st12(pr(h) + 12 * slot, n);
+        if (slot >= 0 && slot < 6) st12(pr(h) + SM::HS * slot, n);
       }
       w.sync();
     }
@@ -795,7 +799,7 @@ struct PdipmFastT {
         double dy;
         if constexpr (kTm) {
           double nr[12];
-          ld12(sm + SM::OFF_P5F + 12 * rr, nr);
+          ld12(sm + SM::OFF_P5F + SM::FS * rr, nr);
           double q0 = 0.0, q1 = 0.0, q2 = 0.0;
 #pragma unroll
           for (int m = 0; m < 12; m += 3) { q0 = fma(-nr[m], bv[m], q0); q1 = fma(-nr[m + 1], bv[m + 1], q1); q2 = fma(-nr[m + 2], bv[m + 2], q2); }
