@@ -285,10 +285,11 @@ int srbd_mpc_solve(srbd_ctx* ctx, const double* const* in17, const float* rotati
 int srbd_mpc_solve_warm(srbd_ctx* ctx, const double* const* in17, const float* rotation_body, int B,
                         int iters, double tol, int mode, const int* reset, float* wrench, double* x_io, double* s_out,
                         double* z_io, double* y_io, double* res_out, int* iters_done, void* stream);
-/* the same with HOST buffers, synchronous.  Page-locked (pinned) buffers are read and written over PCIe by
- * the kernels themselves (UVA mapping); pageable ones are staged with cudaMemcpyAsync.  The batch is cut into
- * chunks that alternate between two internal streams; a prefetch kernel that co-resides with the running
- * solve pulls the next chunk's inputs into device staging, so that its transfer overlaps that solve.  in17_host[1] / [2] (x, u: the linearisation
+/* the same with HOST buffers, synchronous.  The batch is cut into chunks that alternate between two internal streams.
+ * Page-locked (pinned) buffers: the first chunk's inputs are pulled into device staging by one prefetch kernel (coalesced
+ * reads over PCIe through the UVA mapping), the later chunks' by the copy engine while the previous chunk solves, and the
+ * wrench is written to the host buffer by the solve kernel itself; pageable buffers are staged with cudaMemcpyAsync in
+ * both directions.  in17_host[1] / [2] (x, u: the linearisation
  * point, dead for this LTV-linear problem) may be NULL = all ones, the constant the reference call
  * site passes (mpc_controller_cusadi.py:55-56); the same holds for in17[1] / [2] of srbd_qp_form
  * and srbd_mpc_solve. */
