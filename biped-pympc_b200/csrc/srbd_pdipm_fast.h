@@ -769,7 +769,7 @@ struct PdipmFastT {
       const int j1 = h ? i1[0] : i0[0], j2 = h ? i1[1] : i0[1], j3 = h ? i1[2] : i0[2];
       double* vnb = vy + (h ? 108 : 0);
       const R* Pnb = P(h ? 9 : 0);
-#pragma unroll 1
+#pragma unroll    // unrolled (slot numbers and trip flags become immediates): -0.8 % each
       for (int t = 1; t < 6; ++t) {
         const bool act = (t < 5) || (h == 0);
         unsigned tq[24];
@@ -808,7 +808,7 @@ struct PdipmFastT {
         if (h == 0 && r < 12) vk[rr] = dy;
         w.sync();
       }
-#pragma unroll 1
+#pragma unroll    // unrolled (slot numbers and trip flags become immediates): -0.8 % each
       for (int t = 1; t < 6; ++t) {
         const double* yn = vk;                  // the block solved in the previous trip
         // the bottom half has four blocks for the top half's five.  Packed storage: it idles in the last trip.  Tensor
