@@ -974,3 +974,28 @@ def test_general_kernel_matches_the_cusadi_kernel_on_random_values():
     for i in range(4):
         got, want = out[i].cpu().numpy(), ref.outputs_sparse[i].cpu().numpy()
         assert max(rel_err(got[e], want[e]) for e in range(B)) < 1e-8, i
+
+
+@pytest.mark.gpu
+def test_two_contexts_on_two_streams_share_the_gpu():
+    """Two contexts launching the persistent solve kernel on two streams at once: every CTA allocates all 512
+    tensor-memory columns of its SM (and all of its shared memory), so the second kernel's CTAs can only become resident as
+    the first one's leave -- nothing may deadlock, and both results equal the ones computed one after the other."""
+    B = 3000
+    batches = [bp.workload.make_batch(B, seed=500 + i) for i in range(2)]
+    ctxs = [bp.Context(B) for _ in range(2)]
+    devs = [(_dev(inp), torch.as_tensor(rot, dtype=torch.float32, device=DEV)) for inp, rot in batches]
+    want = [c.solve(i, r, num_calls=1, iters_per_call=5, want_iterates=True)[:2] for c, (i, r) in zip(ctxs, devs)]
+    want = [(w.clone(), x.clone()) for w, x in want]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    got = [None, None]
+    for rep in range(3):
+        for k in range(2):
+            with torch.cuda.stream(streams[k]):
+                got[k] = ctxs[k].solve(devs[k][0], devs[k][1], num_calls=1, iters_per_call=5, want_iterates=True)[:2]
+        torch.cuda.synchronize()
+        for k in range(2):
+            assert torch.equal(got[k][0], want[k][0]) and torch.equal(got[k][1], want[k][1])
+    for c in ctxs:
+        c.close()
